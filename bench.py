@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: batched Schwarzschild null-geodesic integration (BASELINE.json metric
+"geodesic rays/s (1024^2 x 5 spp Schwarzschild)").
+
+    python bench.py --gpus N --steps K --warmup W              # this framework (sm_100a kernel)
+    python bench.py --impl reference --steps K --warmup W      # the reference's CPU method on host cores
+
+One "step" = one pass of the hot path over one frame's batch of rays (config 2: 5 242 880 rays).  At N > 1
+(torchrun) every rank integrates its own frame of the orbiting-camera animation (config 4: frames shard
+across GPUs, no data-path collective) => weak scaling; value = rays of all ranks / max-over-ranks time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, SPP = 1024, 1024, 5
+FLOP_FIXED, FLOP_PER_ATTEMPT = 230.0, 760.0  # FLOP(ray) = 230 + 760 * n_attempt
+NOMINAL_FP64_TFLOPS = 37.2                   # 148 SM x 64 FMA/clk x 2 x 1.965 GHz
+
+
+def frame_rays(frame_index: int, width=W, height=H, spp=SPP, first=0, count=None):
+    """Entry positions/directions of one frame of the orbiting-camera animation (config 4; frame 0 = config 2)."""
+    from blackhole_geodesic_calculator_b200 import raygen
+    az = math.radians(3.6 * frame_index)
+    c0 = np.array(raygen.CFG_CAMERA_POS)
+    ca, sa = math.cos(az), math.sin(az)
+    cam = np.array([ca * c0[0] - sa * c0[1], sa * c0[0] + ca * c0[1], c0[2]])
+    return raygen.config_bundle(width, height, spp, jitter="philox", cam_pos=tuple(cam), first_ray=first,
+                                n_rays=count)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline_sample(n_sample_stride=256):
+    """Bounded sample of the same workload for the CPU arm: every 256th ray of frame 0 (20 480 rays)."""
+    pos, d = frame_rays(0)
+    sel = np.arange(0, pos.shape[0], n_sample_stride)
+    return pos[sel], d[sel]
+
+
+def time_reference(pos, d, processes):
+    """The reference's method (sympy RHS + scipy.solve_ivp RK45, one Python call per ray) on host cores."""
+    import multiprocessing as mp
+    from oracle import schwarzschild_ref as R
+    R._build_rhs()  # the sympy derivation happens once per frame in the reference (RRE.py:134): not timed
+    pool = mp.get_context("fork").Pool(processes)
+    try:
+        R.trace_pool(pos[:processes * 8], d[:processes * 8], processes, chunk=8, pool=pool)  # warm the workers
+        t0 = time.perf_counter()
+        out = R.trace_pool(pos, d, processes, chunk=max(16, min(256, pos.shape[0] // (4 * processes))), pool=pool)
+        dt = time.perf_counter() - t0
+    finally:
+        pool.close()
+        pool.join()
+    return pos.shape[0] / dt, dt, out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    pos, d = cpu_baseline_sample()
+    # size the per-step sample so that steps+warmup finish in a few minutes: ~20 s of all-core work per step
+    rates = []
+    per_step = pos.shape[0]
+    probe_rate, _, _ = time_reference(pos[:max(cores * 16, 256)], d[:max(cores * 16, 256)], cores)
+    per_step = int(min(per_step, max(cores * 16, probe_rate * 15.0)))
+    t_all = 0.0
+    for i in range(args.warmup + args.steps):
+        r, dt, _ = time_reference(pos[:per_step], d[:per_step], cores)
+        if i >= args.warmup:
+            rates.append(r)
+            t_all += dt
+    value = per_step * len(rates) / t_all
+    line = {
+        "impl": "reference", "metric": "geodesic rays/s (1024^2 x 5 spp Schwarzschild frame)", "value": value,
+        "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_all / len(rates), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "config 2: 1024x1024x5spp Schwarzschild frame, M=1, r_sphere=60M, rtol=1e-3, "
+                               "atol=1e-6 (bounded sample)", "rays_per_step": per_step},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": f"first {per_step} of the 1/256 strided subsample of frame 0; restated "
+                                   "reference method (sympy RHS + scipy.solve_ivp RK45 per ray, multiprocessing "
+                                   "Pool over all cores); curvedpy itself is absent"},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from blackhole_geodesic_calculator_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = W * H * SPP
+    pos_h, dir_h = frame_rays(rank)  # frame index = rank: frames shard across GPUs
+    # pinned host buffers for the end-to-end leg
+    pin_pos, pin_dir = api.pinned_empty((n, 3)), api.pinned_empty((n, 3))
+    pin_pos[:] = pos_h
+    pin_dir[:] = dir_h
+    pin_op, pin_od = api.pinned_empty((n, 3)), api.pinned_empty((n, 3))
+    pin_st = api.pinned_empty((n,), np.int32)
+    pos = torch.from_numpy(pos_h).to(dev)
+    d = torch.from_numpy(dir_h).to(dev)
+    exit_pos, exit_dir = torch.empty_like(pos), torch.empty_like(pos)
+    status = torch.empty(n, dtype=torch.int32, device=dev)
+    counters = torch.empty((2, n), dtype=torch.int32, device=dev)
+    params = api.make_params(mode=args.mode, refill_threshold=args.threshold)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(with_counters=False):
+        api.trace_device(pos.data_ptr(), d.data_ptr(), exit_pos.data_ptr(), exit_dir.data_ptr(), status.data_ptr(),
+                         counters.data_ptr() if with_counters else None, None, n, api.LAYOUT_AOS, params, local,
+                         stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # attempts per ray (kernel's own counters) for the algorithmic-FLOP figure; untimed
+    step(with_counters=True)
+    torch.cuda.synchronize(dev)
+    att, acc, integ = api.sum_counters(counters.data_ptr(), status.data_ptr(), n, local, stream.cuda_stream)
+    flop_per_launch = FLOP_FIXED * integ + FLOP_PER_ATTEMPT * att
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = api.launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record(stream)
+    for e0, e1 in evs:
+        e0.record(stream)
+        step()
+        e1.record(stream)
+    t_end.record(stream)
+    barrier()
+    launches = api.launch_count() - launches0
+    total_ms = t_start.elapsed_time(t_end)
+    kern_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end-to-end through the public host API: pinned numpy in -> H2D -> trace -> D2H -> pinned numpy out
+    lib_params = params
+    from blackhole_geodesic_calculator_b200 import _lib
+    import ctypes
+    lib = _lib.load()
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+
+    def e2e_step():
+        _lib.check(lib.bhg_trace_schwarzschild_f64_host(p(pin_pos), p(pin_dir), p(pin_op), p(pin_od), p(pin_st), None,
+                                                        n, ctypes.byref(lib_params), local))
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = float(t[0]), float(t[1])
+    value = world * n * args.steps / (total_ms * 1e-3)
+    e2e_value = world * n * e2e_steps / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        kavg = float(np.mean(kern_ms))
+        try:
+            peak_tf, clk_est = api.fp64_peak_tflops(local)
+        except Exception:
+            peak_tf, clk_est = None, None
+        achieved_tf = flop_per_launch / (kavg * 1e-3) / 1e12
+        peak = peak_tf or NOMINAL_FP64_TFLOPS
+        line = {
+            "metric": "geodesic rays/s (1024^2 x 5 spp Schwarzschild frame)", "value": value, "unit": "rays/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "config 2: 1024x1024x5spp Schwarzschild frame (5242880 rays/GPU/step), M=1, "
+                                   "r_sphere=60M, rtol=1e-3, atol=1e-6, camera (120,-80,40)M fov 0.6, Philox jitter "
+                                   "seed 42; at N>1 rank r integrates animation frame r (config 4, camera azimuth "
+                                   "+3.6 deg/frame)",
+                       "mode": args.mode, "refill_threshold": args.threshold or 32,
+                       "rays_per_step_per_gpu": n, "cache": "inputs+outputs 525 MB per step > 126 MB L2 (no flush)",
+                       "mean_attempts_per_ray": att / n},
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n * 48, "d2h_bytes_per_step": n * 52,
+                    "steps": e2e_steps, "api": "bhg_trace_schwarzschild_f64_host (pinned numpy in/out, chunked "
+                                               "H2D/trace/D2H pipeline)"},
+            "gpu_launches": int(launches),
+            "kernel_ms": {"mean": kavg, "min": float(np.min(kern_ms)), "max": float(np.max(kern_ms))},
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak,
+                         "peak_source": ("on-box DFMA microbenchmark (MEASURED_PEAKS.json has no FP64 entry); "
+                                         f"nominal {NOMINAL_FP64_TFLOPS}") if peak_tf else "nominal (148 SM x 64 FMA/clk x 2 x 1.965 GHz)",
+                         "frac_of_nominal": achieved_tf / NOMINAL_FP64_TFLOPS,
+                         "algorithmic_flop_per_launch": flop_per_launch,
+                         "hbm_gbs_achieved": n * 100 / (kavg * 1e-3) / 1e9,
+                         "traffic": None, "dfma_clock_mhz_est": clk_est},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            cpos, cdir = cpu_baseline_sample()
+            m = int(min(cpos.shape[0], max(256, 250 * cores * 12)))  # ~12 s at ~250 rays/s/core
+            rate, dt, _ = time_reference(cpos[:m], cdir[:m], cores)
+            line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
+                                    "sample": f"first {m} rays of the 1/256 strided subsample of frame 0 in {dt:.1f} s; "
+                                              "restated reference method (sympy RHS + scipy.solve_ivp RK45 per ray, "
+                                              "multiprocessing Pool over all cores)"}
+            try:
+                from oracle import port
+                t0 = time.perf_counter()
+                port.trace(cpos, cdir)
+                line["cpu_baseline"]["c_port_rays_per_s_all_cores"] = cpos.shape[0] / (time.perf_counter() - t0)
+            except Exception as e:  # the C port is optional information
+                line["cpu_baseline"]["c_port_error"] = str(e)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="parity", choices=["parity", "plane"])
+    ap.add_argument("--threshold", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

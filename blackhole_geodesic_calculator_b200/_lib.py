@@ -1,0 +1,84 @@
+"""ctypes loader for the C-ABI shared library (include/bhgeo.h).
+
+Deliberately torch-free so it imports in Blender's bundled CPython (numpy only).  There is no CPU
+fallback: if the library is missing or no sm_100 device is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libbhgeo.so")
+
+
+class BhgParams(ctypes.Structure):
+    """Mirror of `struct bhg_params` (include/bhgeo.h)."""
+    _fields_ = [
+        ("M", ctypes.c_double),
+        ("r_sphere", ctypes.c_double),
+        ("rtol", ctypes.c_double),
+        ("atol", ctypes.c_double),
+        ("max_step", ctypes.c_double),
+        ("eps_horizon", ctypes.c_double),
+        ("lambda_max", ctypes.c_double),
+        ("mode", ctypes.c_int32),
+        ("refill_threshold", ctypes.c_int32),
+    ]
+
+
+class BhgError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"bhgeo error {code}: {message}")
+        self.code = code
+
+
+# every symbol include/bhgeo.h declares, with its ctypes signature
+_P = ctypes.c_void_p
+_SIGNATURES = {
+    "bhg_default_params": (None, [ctypes.POINTER(BhgParams)]),
+    "bhg_trace_schwarzschild_f64": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, ctypes.c_int32,
+                                                   ctypes.POINTER(BhgParams), ctypes.c_int32, _P]),
+    "bhg_trace_schwarzschild_f64_host": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, ctypes.c_int64,
+                                                        ctypes.POINTER(BhgParams), ctypes.c_int32]),
+    "bhg_host_alloc": (_P, [ctypes.c_int64]),
+    "bhg_host_free": (None, [_P]),
+    "bhg_sum_counters": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int32, _P,
+                                        ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
+                                        ctypes.POINTER(ctypes.c_int64)]),
+    "bhg_launch_count": (ctypes.c_int64, []),
+    "bhg_selftest": (ctypes.c_int, [ctypes.c_int32, ctypes.POINTER(ctypes.c_double)]),
+    "bhg_fp64_peak_tflops": (ctypes.c_int, [ctypes.c_int32, ctypes.POINTER(ctypes.c_double),
+                                            ctypes.POINTER(ctypes.c_double)]),
+    "bhg_last_error_string": (ctypes.c_char_p, []),
+    "bhg_version": (ctypes.c_int, []),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def load():
+    """Load lib/libbhgeo.so; raises (loudly) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in _SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the ABI and the header drifted apart
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().bhg_last_error_string()
+        raise BhgError(rc, msg.decode("utf-8", "replace") if msg else "")

@@ -1,0 +1,152 @@
+"""`trace()` — the batched drop-in for the reference's per-ray curvedpy call.
+
+Replaces, for a whole frame or tile at once,
+  k_xyz, x_xyz, result = self.GeoInt.calc_trajectory(k0_xyz, x0_xyz, max_step=..., curve_end=..., ...)
+      (/root/reference/raytracer/RelativisticRenderEngine.py:293-294, end state :307-308, status :296-297)
+  x, y, z, end_loc, end_dir, mes = self.SW.ray_trace(direction, loc_hit=loc, ...)
+      (/root/reference/raytracer/LimitedRelativisticRenderEngine.py:273-278, status :308-314)
+with
+  exit_pos, exit_dir, status = trace(entry_pos[N,3], entry_dir[N,3], M, r_sphere, rtol, atol)
+
+numpy in / numpy out goes through the host C entry point; torch CUDA tensors in / out stay on the device
+(torch is optional and only imported when a tensor is passed).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import numpy as np
+
+from . import _lib
+from ._lib import BhgParams
+
+ESCAPED, CAPTURED, START_INSIDE_HOLE, LAMBDA_EXHAUSTED, STEP_FAILED = 0, 1, 2, 3, 4
+STATUS_NAMES = {0: "ESCAPED", 1: "CAPTURED", 2: "START_INSIDE_HOLE", 3: "LAMBDA_EXHAUSTED", 4: "STEP_FAILED"}
+MODES = {"parity": 0, "plane": 1}
+LAYOUT_SOA, LAYOUT_AOS = 0, 1
+
+
+def make_params(M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, max_step=math.inf, eps_horizon=0.01,
+                lambda_max=None, mode="parity", refill_threshold=0) -> BhgParams:
+    if mode not in MODES:
+        raise ValueError(f"mode must be one of {sorted(MODES)}, got {mode!r}")
+    if max_step is None or max_step == -1:  # the reference maps -1 to inf (RelativisticRenderEngine.py:59-60)
+        max_step = math.inf
+    return BhgParams(float(M), float(r_sphere), float(rtol), float(atol), float(max_step), float(eps_horizon),
+                     0.0 if lambda_max is None else float(lambda_max), MODES[mode], int(refill_threshold))
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def trace(entry_pos, entry_dir, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, *, max_step=math.inf,
+          eps_horizon=0.01, lambda_max=None, mode="parity", refill_threshold=0, device=0,
+          return_counters=False):
+    """Integrate N Schwarzschild null geodesics from sphere entry to exit or capture.
+
+    entry_pos, entry_dir : [N,3] float64, BH-centred position and coordinate direction (numpy arrays on the
+        host, or torch CUDA tensors, which are processed in place on their device and stream).
+    Returns (exit_pos[N,3], exit_dir[N,3] unit-norm, status[N] int32) and, with return_counters, an
+    int32 [2,N] array of (RK45 attempts, accepted steps).
+    """
+    params = make_params(M, r_sphere, rtol, atol, max_step, eps_horizon, lambda_max, mode, refill_threshold)
+    if _is_torch(entry_pos):
+        return _trace_torch(entry_pos, entry_dir, params, return_counters)
+    lib = _lib.load()
+    pos = np.ascontiguousarray(entry_pos, dtype=np.float64)
+    dirs = np.ascontiguousarray(entry_dir, dtype=np.float64)
+    if pos.ndim != 2 or pos.shape[1] != 3 or dirs.shape != pos.shape:
+        raise ValueError(f"entry_pos and entry_dir must both be [N,3]; got {pos.shape} and {dirs.shape}")
+    n = pos.shape[0]
+    exit_pos = np.empty((n, 3), dtype=np.float64)
+    exit_dir = np.empty((n, 3), dtype=np.float64)
+    status = np.empty(n, dtype=np.int32)
+    counters = np.empty((2, n), dtype=np.int32) if return_counters else None
+    p = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+    _lib.check(lib.bhg_trace_schwarzschild_f64_host(p(pos), p(dirs), p(exit_pos), p(exit_dir), p(status),
+                                                    p(counters), n, ctypes.byref(params), int(device)))
+    if return_counters:
+        return exit_pos, exit_dir, status, counters
+    return exit_pos, exit_dir, status
+
+
+def _trace_torch(entry_pos, entry_dir, params, return_counters):
+    import torch
+
+    if not (entry_pos.is_cuda and entry_dir.is_cuda):
+        raise ValueError("torch inputs must be CUDA tensors (pass numpy arrays for host data)")
+    pos = entry_pos.to(torch.float64).contiguous()
+    dirs = entry_dir.to(torch.float64).contiguous()
+    if pos.ndim != 2 or pos.shape[1] != 3 or dirs.shape != pos.shape:
+        raise ValueError("entry_pos and entry_dir must both be [N,3]")
+    n = pos.shape[0]
+    dev = pos.device
+    exit_pos = torch.empty_like(pos)
+    exit_dir = torch.empty_like(pos)
+    status = torch.empty(n, dtype=torch.int32, device=dev)
+    counters = torch.empty((2, n), dtype=torch.int32, device=dev) if return_counters else None
+    trace_device(pos.data_ptr(), dirs.data_ptr(), exit_pos.data_ptr(), exit_dir.data_ptr(), status.data_ptr(),
+                 counters.data_ptr() if counters is not None else None, None, n, LAYOUT_AOS, params,
+                 dev.index or 0, torch.cuda.current_stream(dev).cuda_stream)
+    if return_counters:
+        return exit_pos, exit_dir, status, counters
+    return exit_pos, exit_dir, status
+
+
+def trace_device(in_ptr, in_dir_ptr, out_ptr, out_dir_ptr, status_ptr, counters_ptr, order_ptr, n, layout,
+                 params: BhgParams, device=0, stream=0):
+    """Raw device-pointer call (asynchronous on `stream`); the benchmark's hot call."""
+    lib = _lib.load()
+    _lib.check(lib.bhg_trace_schwarzschild_f64(in_ptr, in_dir_ptr, out_ptr, out_dir_ptr, status_ptr, counters_ptr,
+                                               order_ptr, int(n), int(layout), ctypes.byref(params), int(device),
+                                               stream or None))
+
+
+def sum_counters(counters_ptr, status_ptr, n, device=0, stream=0):
+    lib = _lib.load()
+    a, b, c = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+    _lib.check(lib.bhg_sum_counters(counters_ptr, status_ptr, int(n), int(device), stream or None,
+                                    ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+    return a.value, b.value, c.value
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array backed by page-locked host memory (fast, asynchronous staging in the host entry point)."""
+    lib = _lib.load()
+    dtype = np.dtype(dtype)
+    count = int(np.prod(shape))
+    nbytes = max(count * dtype.itemsize, 1)
+    ptr = lib.bhg_host_alloc(nbytes)
+    if not ptr:
+        raise MemoryError("bhg_host_alloc failed: " + lib.bhg_last_error_string().decode())
+    buf = (ctypes.c_char * nbytes).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+    _PINNED[arr.__array_interface__["data"][0]] = (ptr, buf)
+    return arr
+
+
+_PINNED: dict = {}
+
+
+def pinned_free(arr):
+    key = arr.__array_interface__["data"][0]
+    ptr, _ = _PINNED.pop(key)
+    _lib.load().bhg_host_free(ptr)
+
+
+def launch_count():
+    return int(_lib.load().bhg_launch_count())
+
+
+def selftest(device=0):
+    out = (ctypes.c_double * 4)()
+    rc = _lib.load().bhg_selftest(int(device), out)
+    return rc, list(out)
+
+
+def fp64_peak_tflops(device=0):
+    tf, mhz = ctypes.c_double(0), ctypes.c_double(0)
+    _lib.check(_lib.load().bhg_fp64_peak_tflops(int(device), ctypes.byref(tf), ctypes.byref(mhz)))
+    return tf.value, mhz.value

@@ -1,0 +1,335 @@
+// C ABI (include/bhgeo.h) over the sm_100a trace kernels.  No torch, no Python: plain pointers and sizes,
+// so the library loads with ctypes.CDLL from any CPython (Blender 4.1's bundled one included,
+// bl_info at /root/reference/raytracer/RelativisticRenderEngine.py:19).
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <vector>
+
+#include "../../include/bhgeo.h"
+#include "trace_kernel.cuh"
+#include "aux_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define BHG_CUDA(call)                                                                                 \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            int code_ = (e_ == cudaErrorMemoryAllocation) ? BHG_ERR_OUT_OF_MEMORY                      \
+                        : (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ||             \
+                           e_ == cudaErrorInvalidDevice)                                               \
+                            ? BHG_ERR_NO_DEVICE                                                        \
+                            : BHG_ERR_CUDA;                                                            \
+            return fail(code_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                              \
+    } while (0)
+
+constexpr int kMaxDevices = 64;
+constexpr int kQueueSlots = 256;
+
+struct DeviceCtx {
+    std::mutex mu;
+    bool ready = false;
+    int sm_count = 0;
+    int blocks_per_sm[2][2] = {{0, 0}, {0, 0}};  // [mode][layout]
+    unsigned long long* queue_slots = nullptr;   // kQueueSlots work-queue heads
+    std::atomic<unsigned> next_slot{0};
+    // staging buffers of the host entry point (grow-only)
+    std::mutex host_mu;
+    void* stage = nullptr;
+    size_t stage_bytes = 0;
+    cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+    long long* totals = nullptr;  // 3 int64 for bhg_sum_counters
+};
+
+DeviceCtx g_ctx[kMaxDevices];
+
+template <int NS, bool AOS>
+int query_occupancy(int* out) {
+    BHG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, bhg::trace_kernel<NS, AOS>, 128, 0));
+    return 0;
+}
+
+int ensure_device(int device, DeviceCtx** out) {
+    if (device < 0 || device >= kMaxDevices) return fail(BHG_ERR_INVALID_ARGUMENT, "device ordinal %d out of range", device);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(BHG_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device >= count) return fail(BHG_ERR_NO_DEVICE, "device %d requested but only %d present", device, count);
+    BHG_CUDA(cudaSetDevice(device));
+    DeviceCtx& c = g_ctx[device];
+    std::lock_guard<std::mutex> lk(c.mu);
+    if (!c.ready) {
+        cudaDeviceProp prop;
+        BHG_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10)
+            return fail(BHG_ERR_NO_DEVICE, "device %d is sm_%d%d; this build contains sm_100a code only", device,
+                        prop.major, prop.minor);
+        c.sm_count = prop.multiProcessorCount;
+        int rc;
+        if ((rc = query_occupancy<8, false>(&c.blocks_per_sm[0][0]))) return rc;
+        if ((rc = query_occupancy<8, true>(&c.blocks_per_sm[0][1]))) return rc;
+        if ((rc = query_occupancy<6, false>(&c.blocks_per_sm[1][0]))) return rc;
+        if ((rc = query_occupancy<6, true>(&c.blocks_per_sm[1][1]))) return rc;
+        BHG_CUDA(cudaMalloc(&c.queue_slots, kQueueSlots * sizeof(unsigned long long)));
+        BHG_CUDA(cudaMalloc(&c.totals, 3 * sizeof(long long)));
+        c.ready = true;
+    }
+    *out = &c;
+    return 0;
+}
+
+int validate(const bhg_params* p, long long n) {
+    if (!p) return fail(BHG_ERR_INVALID_ARGUMENT, "params is NULL");
+    if (n < 0) return fail(BHG_ERR_INVALID_ARGUMENT, "n = %lld is negative", n);
+    if (n > 2147483647LL) return fail(BHG_ERR_INVALID_ARGUMENT, "n = %lld exceeds 2^31-1 rays per call", n);
+    if (!(p->M > 0.0) || !std::isfinite(p->M)) return fail(BHG_ERR_INVALID_ARGUMENT, "M must be finite and > 0");
+    if (!(p->r_sphere > 2.0 * p->M)) return fail(BHG_ERR_INVALID_ARGUMENT, "r_sphere must exceed r_s = 2 M");
+    if (!(p->rtol > 0.0) || !(p->atol >= 0.0)) return fail(BHG_ERR_INVALID_ARGUMENT, "rtol must be > 0 and atol >= 0");
+    if (!(p->max_step > 0.0)) return fail(BHG_ERR_INVALID_ARGUMENT, "max_step must be > 0 (use +inf for unbounded)");
+    if (!(p->eps_horizon >= 0.0)) return fail(BHG_ERR_INVALID_ARGUMENT, "eps_horizon must be >= 0");
+    if (p->mode != BHG_MODE_PARITY && p->mode != BHG_MODE_PLANE)
+        return fail(BHG_ERR_INVALID_ARGUMENT, "unknown mode %d", p->mode);
+    if (p->refill_threshold < 0 || p->refill_threshold > 32)
+        return fail(BHG_ERR_INVALID_ARGUMENT, "refill_threshold must be in 0..32");
+    double lam = p->lambda_max;
+    if (!(lam > 0.0) && !std::isfinite(p->r_sphere))
+        return fail(BHG_ERR_INVALID_ARGUMENT, "lambda_max must be given when r_sphere is infinite");
+    return 0;
+}
+
+int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* out, double* out_dir, int32_t* status,
+                 int32_t* counters, const int32_t* order, long long n, int layout, const bhg_params* p,
+                 cudaStream_t stream) {
+    if (n == 0) return 0;
+    bhg::TraceArgs a;
+    a.in = in; a.in_dir = in_dir; a.out = out; a.out_dir = out_dir;
+    a.status = status; a.counters = counters; a.order = order;
+    a.n = n;
+    a.rs = 2.0 * p->M;
+    a.r_hor = a.rs + p->eps_horizon;
+    a.r_sphere = p->r_sphere;
+    a.has_outer = std::isfinite(p->r_sphere) ? 1 : 0;
+    a.rtol = p->rtol; a.atol = p->atol; a.max_step = p->max_step;
+    a.lambda_max = p->lambda_max > 0.0 ? p->lambda_max : 10.0 * p->r_sphere;
+    a.refill_threshold = p->refill_threshold > 0 ? p->refill_threshold : 32;
+    unsigned slot = c.next_slot.fetch_add(1) % kQueueSlots;
+    a.queue_head = c.queue_slots + slot;
+    BHG_CUDA(cudaMemsetAsync(a.queue_head, 0, sizeof(unsigned long long), stream));
+    const int mode = p->mode, aos = layout == BHG_LAYOUT_AOS ? 1 : 0;
+    long long want_blocks = (n + 127) / 128;
+    long long max_blocks = (long long)c.sm_count * c.blocks_per_sm[mode][aos];
+    int blocks = (int)(want_blocks < max_blocks ? want_blocks : max_blocks);
+    if (mode == BHG_MODE_PARITY) {
+        if (aos) bhg::trace_kernel<8, true><<<blocks, 128, 0, stream>>>(a);
+        else bhg::trace_kernel<8, false><<<blocks, 128, 0, stream>>>(a);
+    } else {
+        if (aos) bhg::trace_kernel<6, true><<<blocks, 128, 0, stream>>>(a);
+        else bhg::trace_kernel<6, false><<<blocks, 128, 0, stream>>>(a);
+    }
+    g_launches.fetch_add(1);
+    BHG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void bhg_default_params(bhg_params* p) {
+    if (!p) return;
+    p->M = 1.0;
+    p->r_sphere = 60.0;
+    p->rtol = 1e-3;
+    p->atol = 1e-6;
+    p->max_step = std::numeric_limits<double>::infinity();
+    p->eps_horizon = 0.01;
+    p->lambda_max = 0.0;
+    p->mode = BHG_MODE_PARITY;
+    p->refill_threshold = 0;
+}
+
+int bhg_trace_schwarzschild_f64(const double* in, const double* in_dir, double* out, double* out_dir,
+                                int32_t* status, int32_t* counters, const int32_t* order, int64_t n,
+                                int32_t layout, const bhg_params* params, int32_t device, void* stream) {
+    int rc = validate(params, n);
+    if (rc) return rc;
+    if (layout != BHG_LAYOUT_SOA && layout != BHG_LAYOUT_AOS) return fail(BHG_ERR_INVALID_ARGUMENT, "unknown layout %d", layout);
+    if (n > 0 && (!in || !out || !status)) return fail(BHG_ERR_INVALID_ARGUMENT, "NULL ray buffer");
+    if (n > 0 && layout == BHG_LAYOUT_AOS && (!in_dir || !out_dir))
+        return fail(BHG_ERR_INVALID_ARGUMENT, "AOS layout needs in_dir and out_dir");
+    DeviceCtx* c;
+    if ((rc = ensure_device(device, &c))) return rc;
+    return launch_trace(*c, in, in_dir, out, out_dir, status, counters, order, n, layout, params, (cudaStream_t)stream);
+}
+
+int bhg_trace_schwarzschild_f64_host(const double* entry_pos, const double* entry_dir, double* exit_pos,
+                                     double* exit_dir, int32_t* status, int32_t* counters, int64_t n,
+                                     const bhg_params* params, int32_t device) {
+    int rc = validate(params, n);
+    if (rc) return rc;
+    if (n > 0 && (!entry_pos || !entry_dir || !exit_pos || !exit_dir || !status))
+        return fail(BHG_ERR_INVALID_ARGUMENT, "NULL ray buffer");
+    DeviceCtx* c;
+    if ((rc = ensure_device(device, &c))) return rc;
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(c->host_mu);
+    // device staging: pos_in | dir_in | pos_out | dir_out | status | counters
+    const size_t vec = (size_t)n * 3 * sizeof(double);
+    const size_t need = 4 * vec + (size_t)n * 3 * sizeof(int32_t) + 1024;
+    if (c->stage_bytes < need) {
+        if (c->stage) cudaFree(c->stage);
+        c->stage = nullptr;
+        c->stage_bytes = 0;
+        BHG_CUDA(cudaMalloc(&c->stage, need));
+        c->stage_bytes = need;
+    }
+    for (auto& s : c->streams)
+        if (!s) BHG_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    char* base = (char*)c->stage;
+    double* d_pin = (double*)base;
+    double* d_din = (double*)(base + vec);
+    double* d_pout = (double*)(base + 2 * vec);
+    double* d_dout = (double*)(base + 3 * vec);
+    int32_t* d_status = (int32_t*)(base + 4 * vec);
+    int32_t* d_cnt = d_status + n;  // 2 n
+    // chunked pipeline over 3 streams: H2D(i+1) overlaps trace(i) overlaps D2H(i-1)
+    const long long chunk = n <= (1 << 16) ? n : (n <= (1 << 20) ? (n + 3) / 4 : (1 << 18));
+    int si = 0;
+    for (long long b = 0; b < n; b += chunk, si = (si + 1) % 3) {
+        const long long m = (n - b < chunk) ? (n - b) : chunk;
+        cudaStream_t s = c->streams[si];
+        BHG_CUDA(cudaMemcpyAsync(d_pin + 3 * b, entry_pos + 3 * b, (size_t)m * 24, cudaMemcpyHostToDevice, s));
+        BHG_CUDA(cudaMemcpyAsync(d_din + 3 * b, entry_dir + 3 * b, (size_t)m * 24, cudaMemcpyHostToDevice, s));
+        // counters of a chunk live at [b, b+m) and [n + b, ...): give the kernel a chunk-local view by
+        // writing attempts/accepted into a 2m block and scattering on the way back
+        int32_t* cnt_chunk = counters ? d_cnt + 2 * b : nullptr;
+        rc = launch_trace(*c, d_pin + 3 * b, d_din + 3 * b, d_pout + 3 * b, d_dout + 3 * b, d_status + b, cnt_chunk,
+                          nullptr, m, BHG_LAYOUT_AOS, params, s);
+        if (rc) return rc;
+        BHG_CUDA(cudaMemcpyAsync(exit_pos + 3 * b, d_pout + 3 * b, (size_t)m * 24, cudaMemcpyDeviceToHost, s));
+        BHG_CUDA(cudaMemcpyAsync(exit_dir + 3 * b, d_dout + 3 * b, (size_t)m * 24, cudaMemcpyDeviceToHost, s));
+        BHG_CUDA(cudaMemcpyAsync(status + b, d_status + b, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+        if (counters) {
+            BHG_CUDA(cudaMemcpyAsync(counters + b, cnt_chunk, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+            BHG_CUDA(cudaMemcpyAsync(counters + n + b, cnt_chunk + m, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    for (auto& s : c->streams) BHG_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+void* bhg_host_alloc(int64_t bytes) {
+    void* p = nullptr;
+    if (bytes <= 0) return nullptr;
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocPortable) != cudaSuccess) {
+        fail(BHG_ERR_OUT_OF_MEMORY, "cudaHostAlloc(%lld) failed", (long long)bytes);
+        return nullptr;
+    }
+    return p;
+}
+
+void bhg_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int bhg_sum_counters(const int32_t* counters_dev, const int32_t* status_dev, int64_t n, int32_t device, void* stream,
+                     int64_t* n_attempt, int64_t* n_accept, int64_t* n_integrated) {
+    DeviceCtx* c;
+    int rc = ensure_device(device, &c);
+    if (rc) return rc;
+    long long h[3] = {0, 0, 0};
+    if (n > 0 && counters_dev && status_dev) {
+        cudaStream_t s = (cudaStream_t)stream;
+        BHG_CUDA(cudaMemsetAsync(c->totals, 0, 3 * sizeof(long long), s));
+        int blocks = (int)((n + 1023) / 1024);
+        if (blocks > c->sm_count * 8) blocks = c->sm_count * 8;
+        bhg::sum_counters_kernel<<<blocks, 256, 0, s>>>(counters_dev, status_dev, n, c->totals);
+        g_launches.fetch_add(1);
+        BHG_CUDA(cudaGetLastError());
+        BHG_CUDA(cudaMemcpyAsync(h, c->totals, sizeof(h), cudaMemcpyDeviceToHost, s));
+        BHG_CUDA(cudaStreamSynchronize(s));
+    }
+    if (n_attempt) *n_attempt = h[0];
+    if (n_accept) *n_accept = h[1];
+    if (n_integrated) *n_integrated = h[2];
+    return 0;
+}
+
+int64_t bhg_launch_count(void) { return g_launches.load(); }
+
+int bhg_selftest(int32_t device, double* out4) {
+    DeviceCtx* c;
+    int rc = ensure_device(device, &c);
+    if (rc) return rc;
+    double* d = nullptr;
+    BHG_CUDA(cudaMalloc(&d, 4 * sizeof(double)));
+    BHG_CUDA(cudaMemset(d, 0, 4 * sizeof(double)));
+    bhg::selftest_kernel<<<64, 256>>>(d);
+    g_launches.fetch_add(1);
+    BHG_CUDA(cudaGetLastError());
+    double h[4];
+    BHG_CUDA(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    if (out4) memcpy(out4, h, sizeof(h));
+    // reciprocal and tenth root to a few ulp; RHS forms agree to rounding; sincos exact by construction
+    if (!(h[0] < 1e-15) || !(h[1] < 4e-15) || !(h[2] < 1e-12)) return fail(BHG_ERR_CUDA, "selftest out of bounds: rcp %.3e root %.3e rhs %.3e", h[0], h[1], h[2]);
+    return 0;
+}
+
+int bhg_fp64_peak_tflops(int32_t device, double* tflops, double* sm_clock_mhz_est) {
+    DeviceCtx* c;
+    int rc = ensure_device(device, &c);
+    if (rc) return rc;
+    double* d = nullptr;
+    BHG_CUDA(cudaMalloc(&d, sizeof(double) * 1024));
+    cudaEvent_t e0, e1;
+    BHG_CUDA(cudaEventCreate(&e0));
+    BHG_CUDA(cudaEventCreate(&e1));
+    const int iters = 4096;
+    const int blocks = c->sm_count * 4, threads = 256;
+    double best_ms = 1e30;
+    for (int rep = 0; rep < 6; rep++) {
+        BHG_CUDA(cudaEventRecord(e0));
+        bhg::dfma_peak_kernel<<<blocks, threads>>>(d, iters, 1.0000001);
+        g_launches.fetch_add(1);
+        BHG_CUDA(cudaEventRecord(e1));
+        BHG_CUDA(cudaEventSynchronize(e1));
+        float ms;
+        BHG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best_ms) best_ms = ms;
+    }
+    BHG_CUDA(cudaGetLastError());
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * threads;  // 16 DFMA per iteration per thread
+    const double tf = flops / (best_ms * 1e-3) / 1e12;
+    if (tflops) *tflops = tf;
+    // 64 FP64 FMA lanes per SM per clock on B200
+    if (sm_clock_mhz_est) *sm_clock_mhz_est = tf * 1e12 / (2.0 * 64.0 * c->sm_count) / 1e6;
+    return 0;
+}
+
+const char* bhg_last_error_string(void) { return g_err; }
+int bhg_version(void) { return BHG_VERSION; }
+
+}  // extern "C"

@@ -1,0 +1,342 @@
+// Batched trace kernel: persistent warps, one thread per ray, rays served from a global work queue.
+//
+// Replaces the reference's per-ray Python loop body (raytracer/RelativisticRenderEngine.py:237 ->
+// spacetime_ray_cast :271-313; raytracer/LimitedRelativisticRenderEngine.py:232 -> blackhole_hit :259-335)
+// for a whole frame or tile in one launch.
+//
+// Scheduling.  Adaptive step counts differ between rays (5 .. 100+ attempts inside one frame), so a warp
+// does not own a fixed set of 32 rays.  Every lane owns one ray at a time; lanes whose ray has terminated
+// park in a *pending* state that keeps the last step's K-stages in registers.  When at least
+// `refill_threshold` lanes are idle (or nobody is running) the warp services all idle lanes together:
+// event root + dense output + exit conversion + store for the pending ones, then a warp-aggregated
+// atomicAdd on the queue head (ballot/popc rank) hands each idle lane its next ray, which is loaded and
+// initialised (entry conversion, null k_t, f0, Hairer initial step).  The divergent finish/init code is
+// thereby executed once per service instead of once per finishing lane, and the RK45 attempt itself is
+// always executed with all running lanes converged.
+#pragma once
+#include "geodesic_core.cuh"
+
+namespace bhg {
+
+struct TraceArgs {
+    const double* in;      // SOA: 6 planes; AOS: pos[n][3]
+    const double* in_dir;  // AOS only: dir[n][3]
+    double* out;           // SOA: 6 planes; AOS: pos[n][3]
+    double* out_dir;       // AOS only
+    int32_t* status;
+    int32_t* counters;     // nullable: [0,n) attempts, [n,2n) accepted
+    const int32_t* order;  // nullable permutation
+    unsigned long long* queue_head;
+    long long n;
+    double rs, r_hor, r_sphere, rtol, atol, max_step, lambda_max;
+    int has_outer;
+    int refill_threshold;
+};
+
+// pending-event encodings (all < LANE_RUNNING)
+constexpr int PEND_H = -2;   // horizon event active in the last step
+constexpr int PEND_E = -3;   // outer-sphere event active
+constexpr int PEND_HE = -5;  // both
+
+template <bool AOS>
+__device__ __forceinline__ void load_ray(const TraceArgs& a, long long idx, double (&x)[3], double (&k)[3]) {
+    if (AOS) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            x[c] = __ldg(a.in + 3 * idx + c);
+            k[c] = __ldg(a.in_dir + 3 * idx + c);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            x[c] = __ldg(a.in + c * a.n + idx);
+            k[c] = __ldg(a.in + (3 + c) * a.n + idx);
+        }
+    }
+}
+
+template <bool AOS>
+__device__ __forceinline__ void store_ray(const TraceArgs& a, long long idx, const double (&x)[3],
+                                          const double (&k)[3], int status, int n_attempt, int n_accept) {
+    if (AOS) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            a.out[3 * idx + c] = x[c];
+            a.out_dir[3 * idx + c] = k[c];
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            a.out[c * a.n + idx] = x[c];
+            a.out[(3 + c) * a.n + idx] = k[c];
+        }
+    }
+    a.status[idx] = status;
+    if (a.counters) {
+        a.counters[idx] = n_attempt;
+        a.counters[a.n + idx] = n_accept;
+    }
+}
+
+// ---- entry conversion (RelativisticRenderEngine.py:289-291: Conversions().convert_xyz_to_sph) -----------
+// returns false when the ray starts at or inside the capture surface
+template <int NS>
+__device__ __forceinline__ bool init_state(const double (&x)[3], const double (&k)[3], double rs, double r_hor,
+                                           double (&y)[NS]);
+
+template <>
+__device__ __forceinline__ bool init_state<8>(const double (&x)[3], const double (&k)[3], double rs, double r_hor,
+                                              double (&y)[8]) {
+    const double rho2 = fma(x[0], x[0], x[1] * x[1]);
+    const double r2 = fma(x[2], x[2], rho2);
+    const double r = sqrt(r2), rho = sqrt(rho2);
+    if (!(r > r_hor)) return false;
+    const double th = acos(x[2] / r);
+    const double ph = atan2(x[1], x[0]);
+    const double xk = fma(x[0], k[0], x[1] * k[1]);
+    const double k_r = fma(x[2], k[2], xk) / r;
+    const double k_th = fma(x[2], xk, -rho2 * k[2]) / (r2 * rho);
+    const double k_ph = fma(x[0], k[1], -x[1] * k[0]) / rho2;
+    const double s = sin(th);
+    const double rm = r - rs;
+    // null condition g_mn k^m k^n = 0, future-directed root (time_like=False, RelativisticRenderEngine.py:134)
+    const double k_t = r * sqrt(fma(k_r, k_r, rm * r * fma(k_ph * k_ph * s, s, k_th * k_th))) / rm;
+    y[0] = k_t; y[1] = 0.0; y[2] = k_r; y[3] = r; y[4] = k_th; y[5] = th; y[6] = k_ph; y[7] = ph;
+    return true;
+}
+
+// orbital-plane frame: e1 = x/|x|, e2 = unit(k - (k.e1) e1); phi measured from e1 inside the plane
+__device__ __forceinline__ void plane_frame(const double (&x)[3], const double (&k)[3], double& r, double& k_r,
+                                            double& wn, double (&e1)[3], double (&e2)[3]) {
+    r = sqrt(fma(x[0], x[0], fma(x[1], x[1], x[2] * x[2])));
+    const double ir = 1.0 / r;
+#pragma unroll
+    for (int c = 0; c < 3; c++) e1[c] = x[c] * ir;
+    k_r = fma(k[0], e1[0], fma(k[1], e1[1], k[2] * e1[2]));
+    double w[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) w[c] = fma(-k_r, e1[c], k[c]);
+    wn = sqrt(fma(w[0], w[0], fma(w[1], w[1], w[2] * w[2])));
+    const double iw = wn > 0.0 ? 1.0 / wn : 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) e2[c] = w[c] * iw;
+}
+
+template <>
+__device__ __forceinline__ bool init_state<6>(const double (&x)[3], const double (&k)[3], double rs, double r_hor,
+                                              double (&y)[6]) {
+    double r, k_r, wn, e1[3], e2[3];
+    plane_frame(x, k, r, k_r, wn, e1, e2);
+    if (!(r > r_hor)) return false;
+    const double k_ph = wn / r;
+    const double rm = r - rs;
+    const double k_t = r * sqrt(fma(k_r, k_r, rm * r * (k_ph * k_ph))) / rm;
+    y[0] = k_t; y[1] = 0.0; y[2] = k_r; y[3] = r; y[4] = k_ph; y[5] = 0.0;
+    return true;
+}
+
+// ---- exit conversion: spherical state -> Cartesian position + unit direction ----------------------------
+template <int NS>
+__device__ __forceinline__ void exit_state(const double (&y)[NS], const double (&x0)[3], const double (&k0)[3],
+                                           double (&xo)[3], double (&ko)[3]);
+
+template <>
+__device__ __forceinline__ void exit_state<8>(const double (&y)[8], const double (&)[3], const double (&)[3],
+                                              double (&xo)[3], double (&ko)[3]) {
+    double st, ct, sp, cp;
+    sincos(y[5], &st, &ct);
+    sincos(y[7], &sp, &cp);
+    const double R = y[3], k_r = y[2], k_th = y[4], k_ph = y[6];
+    xo[0] = R * st * cp;
+    xo[1] = R * st * sp;
+    xo[2] = R * ct;
+    const double a = fma(k_r, st, R * ct * k_th);  // d(rho)/dlambda
+    const double b = R * st * k_ph;                // rho * dphi/dlambda
+    double v[3];
+    v[0] = fma(a, cp, -b * sp);
+    v[1] = fma(a, sp, b * cp);
+    v[2] = fma(k_r, ct, -R * st * k_th);
+    const double inv = 1.0 / sqrt(fma(v[0], v[0], fma(v[1], v[1], v[2] * v[2])));
+#pragma unroll
+    for (int c = 0; c < 3; c++) ko[c] = v[c] * inv;
+}
+
+template <>
+__device__ __forceinline__ void exit_state<6>(const double (&y)[6], const double (&x0)[3], const double (&k0)[3],
+                                              double (&xo)[3], double (&ko)[3]) {
+    double r0, kr0, wn, e1[3], e2[3];
+    plane_frame(x0, k0, r0, kr0, wn, e1, e2);
+    double sp, cp;
+    sincos(y[5], &sp, &cp);
+    const double R = y[3];
+    const double a = fma(y[2], cp, -R * sp * y[4]);
+    const double b = fma(y[2], sp, R * cp * y[4]);
+    const double inv = 1.0 / sqrt(fma(a, a, b * b));
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        xo[c] = R * fma(cp, e1[c], sp * e2[c]);
+        ko[c] = fma(a, e1[c], b * e2[c]) * inv;
+    }
+}
+
+template <int NS>
+__device__ __forceinline__ bool all_finite(const double (&y)[NS]) {
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < NS; i++) ok = ok && isfinite(y[i]);
+    return ok;
+}
+
+template <int NS, bool AOS>
+__global__ void __launch_bounds__(128) trace_kernel(const TraceArgs a) {
+    constexpr int IR = Rhs<NS>::IR;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+
+    double y[NS], K[7][NS], yn[NS];
+    double t = 0.0, h_abs = 0.0;
+    long long idx = -1;
+    int state = LANE_EMPTY;
+    int n_attempt = 0, n_accept = 0;
+    bool rejected = false;
+    bool exhausted = false;  // warp-uniform: queue has no more rays
+    const int T = a.refill_threshold;
+    const double t_bound = a.lambda_max;
+
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+        y[i] = 0.0;
+        yn[i] = 0.0;
+#pragma unroll
+        for (int s = 0; s < 7; s++) K[s][i] = 0.0;
+    }
+
+    while (true) {
+        const unsigned running = __ballot_sync(FULL, state == LANE_RUNNING);
+        const unsigned empty = __ballot_sync(FULL, state == LANE_EMPTY);
+        const unsigned pending = ~(running | empty);
+        bool service;
+        if (exhausted) {
+            if (running == 0u && pending == 0u) break;
+            service = (running == 0u);  // drain: finish everybody together at the very end
+        } else {
+            service = (running == 0u) || (__popc(~running) >= T);
+        }
+
+        if (service) {
+            // ---------------- finish pending lanes ----------------
+            if (state != LANE_RUNNING && state != LANE_EMPTY) {
+                int final_status = state;
+                if (state < LANE_RUNNING) {
+                    // the last accepted step [t, t + h_abs] crossed an event surface (ivp.py:678-697)
+                    const double h = h_abs;
+                    double q[4];
+                    dense_coeffs(K[0][IR], K[2][IR], K[3][IR], K[4][IR], K[5][IR], K[6][IR], q);
+                    double x_h = 2.0, x_e = 2.0;
+                    if (state == PEND_H || state == PEND_HE) x_h = event_root(q, y[IR], h, a.r_hor);
+                    if (state == PEND_E || state == PEND_HE) x_e = event_root(q, y[IR], h, a.r_sphere);
+                    const double x = fmin(x_h, x_e);  // earliest terminal event (ivp.py:117-126)
+                    final_status = (x_h <= x_e) ? CAPTURED : ESCAPED;
+#pragma unroll
+                    for (int i = 0; i < NS; i++) {
+                        double qi[4];
+                        dense_coeffs(K[0][i], K[2][i], K[3][i], K[4][i], K[5][i], K[6][i], qi);
+                        y[i] = dense_eval(qi, y[i], h, x);
+                    }
+                    t = fma(x, h, t);
+                }
+                double x0[3] = {0, 0, 0}, k0[3] = {0, 0, 0}, xo[3], ko[3];
+                if (NS == 6) load_ray<AOS>(a, idx, x0, k0);
+                if (final_status == START_INSIDE_HOLE) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) xo[c] = ko[c] = __longlong_as_double(0x7ff8000000000000LL);
+                } else {
+                    if (!all_finite<NS>(y)) final_status = STEP_FAILED;
+                    exit_state<NS>(y, x0, k0, xo, ko);
+                }
+                store_ray<AOS>(a, idx, xo, ko, final_status, n_attempt, n_accept);
+                state = LANE_EMPTY;
+            }
+            // ---------------- refill idle lanes ----------------
+            if (!exhausted) {
+                const unsigned idle = __ballot_sync(FULL, state == LANE_EMPTY);
+                const int want = __popc(idle);
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(a.queue_head, (unsigned long long)want);
+                base = __shfl_sync(FULL, base, 0);
+                if (base + (unsigned long long)want >= (unsigned long long)a.n) exhausted = true;
+                if (state == LANE_EMPTY) {
+                    const long long slot = (long long)base + __popc(idle & lt_mask);
+                    if (slot < a.n) {
+                        idx = a.order ? (long long)__ldg(a.order + slot) : slot;
+                        double x0[3], k0[3];
+                        load_ray<AOS>(a, idx, x0, k0);
+                        n_attempt = 0;
+                        n_accept = 0;
+                        rejected = false;
+                        t = 0.0;
+                        if (!init_state<NS>(x0, k0, a.rs, a.r_hor, y)) {
+                            state = START_INSIDE_HOLE;
+                        } else if (!all_finite<NS>(y)) {
+                            state = STEP_FAILED;  // singular entry (on the polar axis): scipy refuses such a y0
+                        } else {
+                            Rhs<NS>::eval(y, a.rs, K[0]);  // f0 (rk.py:94)
+                            h_abs = initial_step<NS>(y, K[0], a.rs, a.rtol, a.atol, t_bound, a.max_step);
+                            state = LANE_RUNNING;
+                        }
+                    }
+                }
+            }
+            continue;
+        }
+
+        if (state == LANE_RUNNING) {
+            // ---------------- one RK45 attempt (rk.py:111-176) ----------------
+            const double min_step = min_step_at(t);
+            if (!rejected) {
+                if (h_abs > a.max_step) h_abs = a.max_step;
+                else if (h_abs < min_step) h_abs = min_step;
+            }
+            if (h_abs < min_step) {
+                state = STEP_FAILED;  // TOO_SMALL_STEP; y holds the last accepted state
+            } else {
+                double t_new = t + h_abs;
+                if (t_new - t_bound > 0.0) t_new = t_bound;
+                const double h = t_new - t;
+                h_abs = fabs(h);
+                n_attempt++;
+                const double esum = rk45_attempt<NS>(y, K, yn, h, a.rs, a.rtol, a.atol);
+                const double en2 = esum * (1.0 / NS);  // (RMS error norm)^2
+                if (en2 < 1.0) {
+                    n_accept++;
+                    const double factor = step_factor(en2, 0.2, rejected ? 1.0 : 10.0);
+                    // events on the accepted step (ivp.py:134-158): horizon either direction, sphere upward
+                    const double gh0 = y[IR] - a.r_hor, gh1 = yn[IR] - a.r_hor;
+                    const double ge0 = y[IR] - a.r_sphere, ge1 = yn[IR] - a.r_sphere;
+                    const bool act_h = (gh0 <= 0.0 && gh1 >= 0.0) || (gh0 >= 0.0 && gh1 <= 0.0);
+                    const bool act_e = a.has_outer && (ge0 <= 0.0 && ge1 >= 0.0);
+                    if (act_h || act_e) {
+                        state = act_h ? (act_e ? PEND_HE : PEND_H) : PEND_E;
+                        h_abs = h;  // keep the step length for the dense output
+                    } else {
+                        h_abs *= factor;
+                        t = t_new;
+                        rejected = false;
+#pragma unroll
+                        for (int i = 0; i < NS; i++) {
+                            y[i] = yn[i];
+                            K[0][i] = K[6][i];  // FSAL
+                        }
+                        if (t - t_bound >= 0.0) state = LAMBDA_EXHAUSTED;
+                    }
+                } else {
+                    h_abs *= step_factor(en2, 0.2, 10.0);
+                    rejected = true;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace bhg

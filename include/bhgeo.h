@@ -1,0 +1,126 @@
+/* bhgeo.h — C ABI of the B200-native batched Schwarzschild null-geodesic tracer.
+ *
+ * Drop-in boundary for ONE path of bldevries/blackhole_geodesic_calculator: the per-ray call into
+ * curvedpy's geodesic solver.  The reference has no FFI layer of its own (it is three Blender add-on
+ * scripts calling a pure-Python package); each entry point below names the reference interface it
+ * replaces (paths relative to /root/reference).  INTEGRATION.md shows the ctypes binding a maintainer
+ * adds on the reference side.
+ *
+ * Conventions: geometrised units G = c = 1, horizon r_s = 2 M (raytracer/RelativisticRenderEngine.py:95);
+ * positions are relative to the black-hole centre (RelativisticRenderEngine.py:278,
+ * LimitedRelativisticRenderEngine.py:265); directions are coordinate tangents, normalised on output
+ * (RelativisticRenderEngine.py:371-372 needs |d_z| <= 1).  All buffers are caller-owned.  Functions return
+ * 0 on success and a negative bhg_error on failure (never throw); bhg_last_error_string() describes the
+ * last failure on the calling thread.  Thread-safe: calls may come from any host thread.
+ */
+#ifndef BHGEO_H
+#define BHGEO_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BHG_VERSION 100 /* 0.1.0 */
+
+/* per-ray status codes written to `status` */
+enum bhg_status {
+    BHG_ESCAPED = 0,           /* left the sphere of influence: exit state is on r = r_sphere            */
+    BHG_CAPTURED = 1,          /* crossed r_s + eps_horizon: result['hit_blackhole'] (RRE.py:297, LIM.py:308) */
+    BHG_START_INSIDE_HOLE = 2, /* entry radius <= r_s + eps_horizon: result['start_inside_hole'] (RRE.py:296) */
+    BHG_LAMBDA_EXHAUSTED = 3,  /* affine length lambda_max reached first: mes['error']=='Outside' (LIM.py:311-312);
+                                  the normal ending of the RRE fixed-length call (RRE.py:293-294,307-308)   */
+    BHG_STEP_FAILED = 4        /* step size underflow / non-finite state (scipy status -1)                */
+};
+
+enum bhg_error {
+    BHG_OK = 0,
+    BHG_ERR_INVALID_ARGUMENT = -1,
+    BHG_ERR_CUDA = -2,
+    BHG_ERR_NO_DEVICE = -3,
+    BHG_ERR_OUT_OF_MEMORY = -4
+};
+
+/* integration algorithm */
+enum bhg_mode {
+    BHG_MODE_PARITY = 0, /* 8-state spherical system + scipy RK45 control: reproduces the reference path */
+    BHG_MODE_PLANE = 1   /* optional: 6-state integration in each ray's conserved orbital plane           */
+};
+
+/* memory layout of the ray buffers */
+enum bhg_layout {
+    BHG_LAYOUT_SOA = 0, /* in: 6 planes of n doubles px,py,pz,dx,dy,dz; out: 6 planes px,py,pz,dx,dy,dz  */
+    BHG_LAYOUT_AOS = 1  /* in: pos[n][3], dir[n][3]; out: pos[n][3], dir[n][3] (numpy [N,3] arrays)       */
+};
+
+/* Solver parameters.  Replaces the keyword arguments of curvedpy's calc_trajectory / ray_trace at
+ * RelativisticRenderEngine.py:293-294 and LimitedRelativisticRenderEngine.py:273-278 plus the constructor
+ * argument `mass` (RelativisticRenderEngine.py:134).  rtol/atol default to scipy's 1e-3 / 1e-6 because no
+ * reference engine passes them. */
+typedef struct bhg_params {
+    double M;           /* black-hole mass, r_s = 2 M                                      */
+    double r_sphere;    /* radius of the sphere of influence; +inf = no outer event (RRE)  */
+    double rtol;        /* RK45 relative tolerance                                         */
+    double atol;        /* RK45 absolute tolerance                                         */
+    double max_step;    /* maximum affine step (+inf = unbounded; RRE.py:57-60 maps -1 to inf) */
+    double eps_horizon; /* capture event at r = r_s + eps_horizon                          */
+    double lambda_max;  /* affine-length bound (curve_end, RRE.py:61,294); <= 0 selects 10 r_sphere */
+    int32_t mode;       /* enum bhg_mode                                                   */
+    int32_t refill_threshold; /* warp work queue: idle lanes that trigger a refill, 1..32; 0 = default */
+} bhg_params;
+
+/* Fills *p with the reference defaults (M=1, r_sphere=60, rtol=1e-3, atol=1e-6, max_step=inf,
+ * eps_horizon=0.01, lambda_max=0 -> auto, parity mode). */
+void bhg_default_params(bhg_params* p);
+
+/* Batched trace on DEVICE buffers (what torch / the benchmark call with tensor.data_ptr()).
+ * Replaces N calls of GeoInt.calc_trajectory (RelativisticRenderEngine.py:293-294) or SW.ray_trace
+ * (LimitedRelativisticRenderEngine.py:273-278) and the end-state extraction at
+ * RelativisticRenderEngine.py:296-310 / LimitedRelativisticRenderEngine.py:308-319.
+ *   layout SOA: in = 6*n doubles (planes), out = 6*n doubles (planes)
+ *   layout AOS: in = pos[n][3] then dir[n][3] given as two pointers via in/in_dir; same for out.
+ *   in_dir/out_dir are ignored (may be NULL) for SOA.
+ *   status   : n int32 (enum bhg_status)
+ *   counters : optional (NULL ok) 2*n int32: [0,n) RK45 step attempts, [n,2n) accepted steps
+ *   order    : optional (NULL ok) n int32 permutation: queue slot k processes ray order[k]
+ *   device   : CUDA device ordinal; stream: cudaStream_t (NULL = default stream).  Asynchronous on `stream`. */
+int bhg_trace_schwarzschild_f64(const double* in, const double* in_dir, double* out, double* out_dir,
+                                int32_t* status, int32_t* counters, const int32_t* order, int64_t n,
+                                int32_t layout, const bhg_params* params, int32_t device, void* stream);
+
+/* Same, on HOST [N,3] arrays (numpy, Blender's bundled Python): stages H2D, traces, stages D2H, and returns
+ * when the results are in the host buffers.  Pinned buffers (bhg_host_alloc) are copied asynchronously in
+ * overlapping chunks.  counters may be NULL. */
+int bhg_trace_schwarzschild_f64_host(const double* entry_pos, const double* entry_dir, double* exit_pos,
+                                     double* exit_dir, int32_t* status, int32_t* counters, int64_t n,
+                                     const bhg_params* params, int32_t device);
+
+/* Pinned host memory for the staging path (optional convenience). */
+void* bhg_host_alloc(int64_t bytes);
+void bhg_host_free(void* p);
+
+/* Totals of the last completed trace on `device` from the calling thread's point of view: sum of RK45
+ * attempts and of RHS evaluations (nfev = 2 + 6 attempts per integrated ray) — used for roofline
+ * accounting.  Only valid if the trace was given a `counters` buffer; otherwise returns zeros. */
+int bhg_sum_counters(const int32_t* counters_dev, const int32_t* status_dev, int64_t n, int32_t device,
+                     void* stream, int64_t* n_attempt, int64_t* n_accept, int64_t* n_integrated);
+
+/* Number of kernels this library has launched in this process (all threads). */
+int64_t bhg_launch_count(void);
+
+/* Device-side numerical self-test of the FP64 building blocks (reciprocal, inverse tenth root, RHS against
+ * IEEE division form).  Writes max relative errors to out[0..3]; returns 0 if all are within bounds. */
+int bhg_selftest(int32_t device, double* out4);
+
+/* FP64 FMA throughput microbenchmark (dependent-free DFMA chains, all SMs), in TFLOP/s; used as the
+ * measured roofline denominator because MEASURED_PEAKS.json carries no FP64 entry. */
+int bhg_fp64_peak_tflops(int32_t device, double* tflops, double* sm_clock_mhz_est);
+
+const char* bhg_last_error_string(void);
+int bhg_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BHGEO_H */

@@ -1,0 +1,65 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# stated parity tolerances (BASELINE.json north_star): 1e-6 relative in position (relative to the sphere
+# radius / scene scale), 1e-6 rad in direction; status bit-exact outside |b - 3*sqrt(3) M| <= 1e-2 M
+POS_RTOL = 1e-6
+DIR_ATOL = 1e-6
+B_CRIT_BAND = 1e-2
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    import __graft_entry__ as g
+    g.build()
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN, name))
+    return {k: z[k] for k in z.files}
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return load_golden
+
+
+def golden_kwargs(g):
+    """Solver keyword arguments stored with a golden file."""
+    kw = dict(M=float(g["M"]), r_sphere=float(g["r_sphere"]), rtol=float(g["rtol"]), atol=float(g["atol"]))
+    if "lambda_max" in g:
+        kw["lambda_max"] = float(g["lambda_max"])
+    if "max_step" in g:
+        kw["max_step"] = float(g["max_step"])
+    return kw
+
+
+def assert_parity(got_pos, got_dir, got_status, ref_pos, ref_dir, ref_status, scale, exclude=None,
+                  pos_rtol=POS_RTOL, dir_atol=DIR_ATOL):
+    """Status bit-exact; exit position/direction within the stated tolerance for rays that terminated on an
+    event or at lambda_max.  `exclude` masks rays inside the stated critical band."""
+    got_status = np.asarray(got_status)
+    ref_status = np.asarray(ref_status)
+    keep = np.ones(len(ref_status), bool) if exclude is None else ~exclude
+    bad = keep & (got_status != ref_status)
+    assert not bad.any(), f"status mismatch on rays {np.nonzero(bad)[0][:10]}: {got_status[bad][:10]} vs {ref_status[bad][:10]}"
+    cmp = keep & np.isin(ref_status, (0, 1, 3))
+    dpos = np.abs(got_pos[cmp] - ref_pos[cmp]).max(initial=0.0) / scale
+    # angle between unit vectors
+    cr = np.linalg.norm(np.cross(got_dir[cmp], ref_dir[cmp]), axis=1)
+    ddir = cr.max(initial=0.0)
+    assert dpos <= pos_rtol, f"exit position differs by {dpos:.3e} (relative to {scale})"
+    assert ddir <= dir_atol, f"exit direction differs by {ddir:.3e} rad"
+    return dpos, ddir

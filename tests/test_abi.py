@@ -1,0 +1,91 @@
+"""CPU tests: the C-ABI library loads, exports every symbol include/bhgeo.h declares, validates arguments
+without a GPU, and fails loudly (no CPU fallback) when no device is present."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+from blackhole_geodesic_calculator_b200 import _lib, api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "bhgeo.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bhg_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_loader_agree():
+    assert header_functions() == _lib.exported_symbols()
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in header_functions():
+        assert hasattr(lib, name), name
+
+
+def test_version_and_defaults():
+    lib = _lib.load()
+    assert lib.bhg_version() == 100
+    p = _lib.BhgParams()
+    lib.bhg_default_params(ctypes.byref(p))
+    assert (p.M, p.r_sphere, p.rtol, p.atol, p.eps_horizon, p.mode) == (1.0, 60.0, 1e-3, 1e-6, 0.01, 0)
+    assert math.isinf(p.max_step) and p.lambda_max == 0.0
+
+
+def test_params_struct_layout():
+    assert ctypes.sizeof(_lib.BhgParams) == 7 * 8 + 2 * 4
+
+
+@pytest.mark.parametrize("kw,frag", [
+    (dict(M=-1.0), "M must be"),
+    (dict(r_sphere=1.0), "r_sphere"),
+    (dict(rtol=0.0), "rtol"),
+    (dict(max_step=0.0), "max_step"),
+    (dict(refill_threshold=33), "refill_threshold"),
+    (dict(r_sphere=math.inf), "lambda_max must be given"),
+])
+def test_argument_validation_needs_no_gpu(kw, frag):
+    pos = np.zeros((4, 3))
+    with pytest.raises(_lib.BhgError) as e:
+        api.trace(pos, pos, **kw)
+    assert e.value.code == -1 and frag in str(e.value)
+
+
+def test_shape_validation():
+    with pytest.raises(ValueError):
+        api.trace(np.zeros((4, 2)), np.zeros((4, 2)))
+    with pytest.raises(ValueError):
+        api.trace(np.zeros((4, 3)), np.zeros((5, 3)))
+    with pytest.raises(ValueError):
+        api.make_params(mode="fast")
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product path must raise, not compute on the CPU."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present")
+    pos = np.array([[-60.0, 0.0, 0.0]])
+    with pytest.raises(_lib.BhgError) as e:
+        api.trace(pos, np.array([[1.0, 0.0, 0.0]]))
+    assert e.value.code == -3 and "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "blackhole_geodesic_calculator_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+                assert "rk45_port" not in text or f.endswith(".md"), f

@@ -1,0 +1,207 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C ABI
+(include/bhgeo.h): the host entry point for numpy arrays, the device entry point for torch tensors.
+
+Tolerances (BASELINE.json north_star): status bit-exact outside |b - 3 sqrt(3) M| <= 1e-2 M; exit position
+within 1e-6 relative (to the sphere radius), exit direction within 1e-6 rad."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import B_CRIT_BAND, assert_parity, golden_kwargs, load_golden
+
+pytestmark = pytest.mark.gpu
+
+B_CRIT = 3.0 * np.sqrt(3.0)
+
+
+@pytest.fixture(scope="module")
+def api():
+    from blackhole_geodesic_calculator_b200 import api as _api
+    rc, errs = _api.selftest(0)
+    print("selftest", rc, errs)
+    assert rc == 0, errs
+    return _api
+
+
+def crit_band(pos, d, M):
+    from blackhole_geodesic_calculator_b200 import raygen
+    b = raygen.conserved_impact_parameter(pos, d, M)
+    return np.abs(b - B_CRIT * M) <= B_CRIT_BAND * M
+
+
+GOLDEN_FILES = ["cfg1_64x64.npz", "cfg5_nearcrit_3d.npz", "cfg5_nearcrit_plane.npz", "cfg3_sample.npz",
+                "tight_16x16.npz", "rre_shape_16x16.npz", "maxstep_8x8.npz", "analytic_kat.npz"]
+
+
+@pytest.mark.parametrize("name", GOLDEN_FILES)
+def test_golden_parity_host_entry(api, name):
+    """CUDA path vs the committed scipy golden vectors, numpy in / numpy out."""
+    g = load_golden(name)
+    kw = golden_kwargs(g)
+    ep, ed, st, cnt = api.trace(g["entry_pos"], g["entry_dir"], return_counters=True, **kw)
+    scale = kw["r_sphere"] if np.isfinite(kw["r_sphere"]) else 50.0
+    band = crit_band(g["entry_pos"], g["entry_dir"], kw["M"])
+    dpos, ddir = assert_parity(ep, ed, st, g["exit_pos"], g["exit_dir"], g["status"], scale, exclude=band)
+    # same discrete algorithm: the step sequence itself must match (nfev = 2 + 6 attempts)
+    integ = ~band & (g["status"] != 2)
+    same = (2 + 6 * cnt[0][integ] == g["nfev"][integ]) & (cnt[1][integ] == g["n_accept"][integ])
+    print(f"{name}: dpos {dpos:.2e} ddir {ddir:.2e} identical step sequences {same.mean() * 100:.2f}% "
+          f"({(~same).sum()} differ)")
+    assert same.mean() >= 0.999
+    assert np.allclose(np.linalg.norm(ed[np.isin(st, (0, 1, 3))], axis=1), 1.0, atol=1e-12)
+
+
+def test_edge_cases(api):
+    g = load_golden("edge_cases.npz")
+    kw = golden_kwargs(g)
+    ep, ed, st = api.trace(g["entry_pos"], g["entry_dir"], **kw)
+    assert np.array_equal(st, g["status"]), (st, g["status"])
+    ok = np.isin(st, (0, 1, 3))
+    assert np.abs(ep[ok] - g["exit_pos"][ok]).max() / 60.0 < 1e-6
+    assert np.abs(ed[ok] - g["exit_dir"][ok]).max() < 1e-6
+    assert np.isnan(ep[st == 2]).all() and np.isnan(ed[st == 2]).all()
+
+
+def test_empty_and_ragged_sizes(api):
+    ep, ed, st = api.trace(np.zeros((0, 3)), np.zeros((0, 3)))
+    assert ep.shape == (0, 3) and st.shape == (0,)
+    g = load_golden("cfg1_64x64.npz")
+    from oracle import port
+    for n in (1, 31, 33, 127, 129, 1000):
+        ep, ed, st = api.trace(g["entry_pos"][:n], g["entry_dir"][:n])
+        assert np.array_equal(st, g["status"][:n])
+        assert np.abs(ep - g["exit_pos"][:n]).max() / 60.0 < 1e-6
+
+
+def test_device_entry_layouts_order_and_thresholds_are_bitwise_identical(api):
+    """Scheduling must not change arithmetic: SoA vs AoS, any refill threshold, any queue order."""
+    import torch
+    g = load_golden("cfg1_64x64.npz")
+    n = g["entry_pos"].shape[0]
+    dev = torch.device("cuda:0")
+    pos = torch.from_numpy(g["entry_pos"]).to(dev)
+    d = torch.from_numpy(g["entry_dir"]).to(dev)
+    base = [t.cpu().numpy() for t in api.trace(pos, d)]
+    assert_parity(base[0], base[1], base[2], g["exit_pos"], g["exit_dir"], g["status"], 60.0,
+                  exclude=crit_band(g["entry_pos"], g["entry_dir"], 1.0))
+    for T in (1, 4, 12, 32):
+        out = [t.cpu().numpy() for t in api.trace(pos, d, refill_threshold=T)]
+        for a, b in zip(base, out):
+            assert np.array_equal(a, b, equal_nan=True), f"threshold {T}"
+    # SoA planes + a random queue order
+    soa_in = torch.cat([pos.t().contiguous(), d.t().contiguous()]).contiguous()  # [6, n]
+    soa_out = torch.empty_like(soa_in)
+    status = torch.empty(n, dtype=torch.int32, device=dev)
+    order = torch.randperm(n, device=dev, dtype=torch.int32)
+    params = api.make_params()
+    api.trace_device(soa_in.data_ptr(), None, soa_out.data_ptr(), None, status.data_ptr(), None, order.data_ptr(),
+                     n, api.LAYOUT_SOA, params, 0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(soa_out[:3].t().cpu().numpy(), base[0], equal_nan=True)
+    assert np.array_equal(soa_out[3:].t().cpu().numpy(), base[1], equal_nan=True)
+    assert np.array_equal(status.cpu().numpy(), base[2])
+
+
+def test_pinned_host_buffers(api):
+    g = load_golden("cfg3_sample.npz")
+    n = g["entry_pos"].shape[0]
+    pos = api.pinned_empty((n, 3))
+    d = api.pinned_empty((n, 3))
+    pos[:] = g["entry_pos"]
+    d[:] = g["entry_dir"]
+    ep, ed, st = api.trace(pos, d)
+    assert_parity(ep, ed, st, g["exit_pos"], g["exit_dir"], g["status"], 60.0)
+    api.pinned_free(pos)
+    api.pinned_free(d)
+
+
+def test_plane_mode_against_its_cpu_restatement_and_analytic(api):
+    from oracle import port
+    g = load_golden("cfg5_nearcrit_3d.npz")
+    ep, ed, st, cnt = api.trace(g["entry_pos"], g["entry_dir"], mode="plane", return_counters=True)
+    o = port.trace(g["entry_pos"], g["entry_dir"], mode=1)
+    band = np.abs(g["b"] - B_CRIT) <= B_CRIT_BAND
+    assert_parity(ep, ed, st, o["exit_pos"], o["exit_dir"], o["status"], 60.0, exclude=band)
+    assert (cnt[0][~band] == o["n_attempt"][~band]).mean() > 0.999
+    # analytic deflection at tight tolerance
+    k = load_golden("analytic_kat.npz")
+    ep, ed, st = api.trace(k["entry_pos"], k["entry_dir"], rtol=1e-12, atol=1e-14, mode="plane")
+    e_in = np.arctan2(k["entry_pos"][:, 1], k["entry_pos"][:, 0])
+    e_out = np.arctan2(ep[:, 1], ep[:, 0])
+    swept = np.mod(e_in - e_out, 2 * np.pi)
+    kk = np.round((k["dphi_analytic"] - swept) / (2 * np.pi))
+    assert np.abs(swept + 2 * np.pi * kk - k["dphi_analytic"]).max() < 5e-8
+
+
+def test_analytic_deflection_parity_mode(api):
+    k = load_golden("analytic_kat.npz")
+    ep, ed, st = api.trace(k["entry_pos"], k["entry_dir"], rtol=1e-12, atol=1e-14)
+    assert (st == 0).all()
+    e_in = np.arctan2(k["entry_pos"][:, 1], k["entry_pos"][:, 0])
+    e_out = np.arctan2(ep[:, 1], ep[:, 0])
+    swept = np.mod(e_in - e_out, 2 * np.pi)
+    kk = np.round((k["dphi_analytic"] - swept) / (2 * np.pi))
+    assert np.abs(swept + 2 * np.pi * kk - k["dphi_analytic"]).max() < 5e-8
+
+
+def test_full_frame_properties_and_subsample_parity(api):
+    """BASELINE config 2 (1024 x 1024 x 5 spp = 5 242 880 rays) at full size: size-independent properties on
+    every ray, and per-ray parity against the oracle on a 1/1024 strided subsample."""
+    import torch
+    from blackhole_geodesic_calculator_b200 import raygen
+    from oracle import port
+    pos, d = raygen.config_bundle(1024, 1024, 5, jitter="philox")
+    n = pos.shape[0]
+    assert n == 5242880
+    dev = torch.device("cuda:0")
+    tp, td = torch.from_numpy(pos).to(dev), torch.from_numpy(d).to(dev)
+    ep, ed, st, cnt = api.trace(tp, td, return_counters=True)
+    torch.cuda.synchronize()
+    att, acc, integ = api.sum_counters(cnt.data_ptr(), st.data_ptr(), n)
+    ep, ed, st, cnt = ep.cpu().numpy(), ed.cpu().numpy(), st.cpu().numpy(), cnt.cpu().numpy()
+    assert att == int(cnt[0].sum()) and acc == int(cnt[1].sum()) and integ == n
+    assert set(np.unique(st)) <= {0, 1}
+    esc = st == 0
+    assert np.abs(np.linalg.norm(ep[esc], axis=1) - 60.0).max() < 1e-9        # exit on the sphere
+    assert np.abs(np.linalg.norm(ep[~esc], axis=1) - 2.01).max() < 1e-9       # capture on r_s + eps
+    assert np.abs(np.linalg.norm(ed, axis=1) - 1.0).max() < 1e-12            # unit directions
+    assert (np.sum(ep[esc] * ed[esc], axis=1) > 0).all()                      # leaving outward
+    # the shadow: captured iff b < b_crit, outside the stated band
+    b = raygen.conserved_impact_parameter(pos, d, 1.0)
+    away = np.abs(b - B_CRIT) > B_CRIT_BAND
+    assert np.array_equal(st[away] == 1, b[away] < B_CRIT)
+    # conserved angular momentum direction: exit state stays in the entry orbital plane
+    nrm = np.cross(pos, d)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    big = b > 1.0
+    assert np.abs(np.sum(nrm * ep, axis=1))[big].max() / 60.0 < 5e-3   # default-tolerance drift only
+    # strided subsample against the oracle
+    sel = np.arange(0, n, 1024)
+    o = port.trace(pos[sel], d[sel])
+    band = ~away[sel]
+    assert_parity(ep[sel], ed[sel], st[sel], o["exit_pos"], o["exit_dir"], o["status"], 60.0, exclude=band)
+    assert (cnt[0][sel][~band] == o["n_attempt"][~band]).mean() > 0.999
+    print(f"full frame: attempts/ray {att / n:.2f}, captured {100 * (~esc).mean():.3f}%")
+
+
+def test_time_reversal_on_gpu(api):
+    g = load_golden("cfg3_sample.npz")
+    ep, ed, st = api.trace(g["entry_pos"], g["entry_dir"], rtol=1e-11, atol=1e-13)
+    esc = st == 0
+    bp, bd, bs = api.trace(ep[esc] * (1 - 1e-12), -ed[esc], rtol=1e-11, atol=1e-13)
+    assert (bs == 0).all()
+    assert np.abs(bp - g["entry_pos"][esc]).max() / 60.0 < 1e-6
+    assert np.abs(bd + g["entry_dir"][esc]).max() < 1e-6
+
+
+def test_error_codes_on_gpu(api):
+    from blackhole_geodesic_calculator_b200 import _lib
+    lib = _lib.load()
+    p = api.make_params()
+    rc = lib.bhg_trace_schwarzschild_f64(None, None, None, None, None, None, None, 8, 1, ctypes.byref(p), 0, None)
+    assert rc == -1 and b"NULL" in lib.bhg_last_error_string()
+    rc = lib.bhg_trace_schwarzschild_f64(None, None, None, None, None, None, None, 0, 7, ctypes.byref(p), 0, None)
+    assert rc == -1
+    rc = lib.bhg_trace_schwarzschild_f64(None, None, None, None, None, None, None, 0, 1, ctypes.byref(p), 63, None)
+    assert rc == -3

@@ -1,0 +1,88 @@
+"""CPU tests: the oracle itself.  The C port (oracle/rk45_port.c) against the golden vectors produced by the
+real scipy path, against the analytic orbit integral, and through conserved quantities."""
+import numpy as np
+import pytest
+
+from conftest import assert_parity, golden_kwargs, load_golden
+from oracle import port
+
+FILES = ["cfg1_64x64.npz", "cfg5_nearcrit_3d.npz", "cfg5_nearcrit_plane.npz", "cfg3_sample.npz",
+         "tight_16x16.npz", "rre_shape_16x16.npz", "maxstep_8x8.npz", "edge_cases.npz", "analytic_kat.npz"]
+
+
+@pytest.mark.parametrize("name", FILES)
+def test_port_matches_scipy_golden(name):
+    g = load_golden(name)
+    kw = golden_kwargs(g)
+    o = port.trace(g["entry_pos"], g["entry_dir"], **kw)
+    # same discrete algorithm: identical step sequence, not just similar answers
+    assert np.array_equal(o["status"], g["status"])
+    assert np.array_equal(o["nfev"], g["nfev"])
+    assert np.array_equal(o["n_accept"], g["n_accept"])
+    scale = kw["r_sphere"] if np.isfinite(kw["r_sphere"]) else 50.0
+    dpos, ddir = assert_parity(o["exit_pos"], o["exit_dir"], o["status"], g["exit_pos"], g["exit_dir"], g["status"],
+                               scale, pos_rtol=5e-7, dir_atol=5e-7)  # round-off amplification reaches 1e-7 on near-critical rays
+    print(name, "dpos", dpos, "ddir", ddir)
+
+
+def test_nfev_identity():
+    g = load_golden("cfg1_64x64.npz")
+    o = port.trace(g["entry_pos"], g["entry_dir"])
+    integrated = o["status"] != 2
+    assert np.array_equal(o["nfev"][integrated], 2 + 6 * o["n_attempt"][integrated])  # SURVEY 8d identity
+
+
+def test_analytic_deflection():
+    g = load_golden("analytic_kat.npz")
+    o = port.trace(g["entry_pos"], g["entry_dir"], rtol=1e-12, atol=1e-14)
+    e_in = np.arctan2(g["entry_pos"][:, 1], g["entry_pos"][:, 0])
+    e_out = np.arctan2(o["exit_pos"][:, 1], o["exit_pos"][:, 0])
+    swept = np.mod(e_in - e_out, 2 * np.pi)
+    k = np.round((g["dphi_analytic"] - swept) / (2 * np.pi))
+    err = np.abs(swept + 2 * np.pi * k - g["dphi_analytic"])
+    assert err.max() < 5e-8, err  # event offset / quadrature noise, SURVEY A.5
+    # exit lies on the sphere, direction is unit
+    assert np.allclose(np.linalg.norm(o["exit_pos"], axis=1), 60.0, rtol=0, atol=1e-9)
+    assert np.allclose(np.linalg.norm(o["exit_dir"], axis=1), 1.0, rtol=0, atol=1e-14)
+
+
+def test_critical_impact_parameter_classification():
+    from blackhole_geodesic_calculator_b200 import raygen
+    pos, d, b = raygen.near_critical_bundle(2000, in_plane=True, seed=3)
+    o = port.trace(pos, d, rtol=1e-10, atol=1e-13)
+    bc = 3 * np.sqrt(3.0)
+    away = np.abs(b - bc) > 1e-3
+    assert np.array_equal(o["status"][away] == 1, b[away] < bc)
+
+
+def test_plane_mode_agrees_with_parity_at_tight_tolerance():
+    g = load_golden("cfg5_nearcrit_3d.npz")
+    a = port.trace(g["entry_pos"], g["entry_dir"], rtol=1e-11, atol=1e-13, mode=0)
+    p = port.trace(g["entry_pos"], g["entry_dir"], rtol=1e-11, atol=1e-13, mode=1)
+    away = np.abs(g["b"] - 3 * np.sqrt(3.0)) > 1e-2
+    assert np.array_equal(a["status"][away], p["status"][away])
+    m = away & (a["status"] == 0)
+    assert np.abs(a["exit_pos"][m] - p["exit_pos"][m]).max() / 60.0 < 1e-5
+    assert np.abs(a["exit_dir"][m] - p["exit_dir"][m]).max() < 1e-5
+
+
+def test_flat_limit_is_a_chord():
+    # M -> 0: straight line through the sphere
+    from blackhole_geodesic_calculator_b200 import raygen
+    pos, d = raygen.config_bundle(8, 8, 1, fov=0.45)
+    o = port.trace(pos, d, M=1e-9, rtol=1e-10, atol=1e-12)
+    chord = -2 * np.sum(pos * d, axis=1)
+    expect = pos + chord[:, None] * d
+    assert np.abs(o["exit_pos"] - expect).max() < 1e-5
+    assert np.abs(o["exit_dir"] - d).max() < 1e-7
+
+
+def test_time_reversal():
+    g = load_golden("cfg3_sample.npz")
+    o = port.trace(g["entry_pos"], g["entry_dir"], rtol=1e-11, atol=1e-13)
+    esc = o["status"] == 0
+    # nudge inside the sphere so the reversed ray starts with an inward step
+    back = port.trace(o["exit_pos"][esc] * (1 - 1e-12), -o["exit_dir"][esc], rtol=1e-11, atol=1e-13)
+    assert (back["status"] == 0).all()
+    assert np.abs(back["exit_pos"] - g["entry_pos"][esc]).max() / 60.0 < 1e-6
+    assert np.abs(back["exit_dir"] + g["entry_dir"][esc]).max() < 1e-6
