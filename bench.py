@@ -91,11 +91,19 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_baseline_sample(n_sample_stride=256):
-    """Bounded sample of the same workload for the CPU arm: every 256th ray of frame 0 (20 480 rays)."""
-    pos, d = frame_rays(0)
-    sel = np.arange(0, pos.shape[0], n_sample_stride)
-    return pos[sel], d[sel]
+_FRAME0 = None
+
+
+def cpu_baseline_sample(target=20480):
+    """Bounded sample of the same workload for the CPU arm: a strided subsample of frame 0 with about
+    `target` rays (stride 256 -> 20 480 rays), so that it covers the whole image including the shadow."""
+    global _FRAME0
+    if _FRAME0 is None:
+        _FRAME0 = frame_rays(0)
+    pos, d = _FRAME0
+    stride = max(1, pos.shape[0] // max(int(target), 1))
+    sel = np.arange(0, pos.shape[0], stride)
+    return pos[sel], d[sel], stride
 
 
 def time_reference(pos, d, processes):
@@ -120,15 +128,15 @@ def run_reference(args):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    pos, d = cpu_baseline_sample()
-    # size the per-step sample so that steps+warmup finish in a few minutes: ~20 s of all-core work per step
+    # size the per-step sample so that steps+warmup finish in a few minutes: ~15 s of all-core work per step
+    pos, d, _ = cpu_baseline_sample(max(cores * 16, 256))
+    probe_rate, _, _ = time_reference(pos, d, cores)
+    pos, d, stride = cpu_baseline_sample(min(20480, max(cores * 16, probe_rate * 15.0)))
     rates = []
     per_step = pos.shape[0]
-    probe_rate, _, _ = time_reference(pos[:max(cores * 16, 256)], d[:max(cores * 16, 256)], cores)
-    per_step = int(min(per_step, max(cores * 16, probe_rate * 15.0)))
     t_all = 0.0
     for i in range(args.warmup + args.steps):
-        r, dt, _ = time_reference(pos[:per_step], d[:per_step], cores)
+        r, dt, _ = time_reference(pos, d, cores)
         if i >= args.warmup:
             rates.append(r)
             t_all += dt
@@ -141,7 +149,7 @@ def run_reference(args):
         "config": {"workload": "config 2: 1024x1024x5spp Schwarzschild frame, M=1, r_sphere=60M, rtol=1e-3, "
                                "atol=1e-6 (bounded sample)", "rays_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": f"first {per_step} of the 1/256 strided subsample of frame 0; restated "
+                         "sample": f"every {stride}th ray of frame 0 ({per_step} rays per step); restated "
                                    "reference method (sympy RHS + scipy.solve_ivp RK45 per ray, multiprocessing "
                                    "Pool over all cores); curvedpy itself is absent"},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -284,11 +292,11 @@ def run_b200(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
-            cpos, cdir = cpu_baseline_sample()
-            m = int(min(cpos.shape[0], max(256, 250 * cores * 12)))  # ~12 s at ~250 rays/s/core
-            rate, dt, _ = time_reference(cpos[:m], cdir[:m], cores)
+            cpos, cdir, stride = cpu_baseline_sample(min(20480, max(256, 250 * cores * 12)))  # ~12 s of work
+            m = cpos.shape[0]
+            rate, dt, _ = time_reference(cpos, cdir, cores)
             line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
-                                    "sample": f"first {m} rays of the 1/256 strided subsample of frame 0 in {dt:.1f} s; "
+                                    "sample": f"every {stride}th ray of frame 0 ({m} rays) in {dt:.1f} s; "
                                               "restated reference method (sympy RHS + scipy.solve_ivp RK45 per ray, "
                                               "multiprocessing Pool over all cores)"}
             try:
