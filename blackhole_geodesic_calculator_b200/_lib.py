@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libbhgeo.so")
+# BHG_LIB selects an alternative build of the same ABI (kernel tuning experiments); default is the in-tree build
+LIB_PATH = os.environ.get("BHG_LIB") or os.path.join(_HERE, "lib", "libbhgeo.so")
 
 
 class BhgParams(ctypes.Structure):

@@ -141,7 +141,7 @@ def launch_count():
 
 
 def selftest(device=0):
-    out = (ctypes.c_double * 4)()
+    out = (ctypes.c_double * 8)()
     rc = _lib.load().bhg_selftest(int(device), out)
     return rc, list(out)
 

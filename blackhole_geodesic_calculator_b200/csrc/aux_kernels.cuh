@@ -37,17 +37,27 @@ __device__ __forceinline__ void atomic_max_double(double* addr, double v) {
 }
 
 // out[0]: max rel. error of fast_rcp vs IEEE 1/a ; out[1]: inv_tenth_root vs pow(a,-0.1) ;
-// out[2]: RHS (reciprocal form) vs the textbook division form ; out[3]: unused (0)
+// out[2]: RHS (reciprocal form) vs the textbook division form ; out[3]: 3-DFMA reciprocal ;
+// out[4]: table sincos vs library sincos (absolute)
 __global__ void selftest_kernel(double* out) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nth = gridDim.x * blockDim.x;
-    double e_rcp = 0, e_root = 0, e_rhs = 0;
+    double e_rcp = 0, e_root = 0, e_rhs = 0, e_rcp3 = 0, e_sc = 0;
     for (int j = gid; j < nth * 16; j += nth) {
         // log-uniform-ish positive and negative operands
         const double u = (j + 0.5) / (nth * 16.0);
         const double a = exp((u - 0.5) * 80.0) * ((j & 1) ? -1.0 : 1.0);
         const double r0 = 1.0 / a, r1 = fast_rcp(a);
         e_rcp = fmax(e_rcp, fabs(r1 - r0) / fabs(r0));
+        e_rcp3 = fmax(e_rcp3, fabs(fast_rcp3(a) - r0) / fabs(r0));
+        {
+            // table sincos vs the library over |x| < 40
+            const double xs = (u - 0.5) * 80.0;
+            double s0, c0, s1, c1;
+            sincos(xs, &s0, &c0);
+            sincos_tab(xs, &s1, &c1);
+            e_sc = fmax(e_sc, fmax(fabs(s1 - s0), fabs(c1 - c0)));
+        }
         const double b = exp((u - 0.5) * 40.0);  // 2e-9 .. 5e8 covers [1e-12,1e8] core range partially
         if (b > 1e-12 && b < 1e8) {
             const double p0 = pow(b, -0.1), p1 = inv_tenth_root(b);
@@ -56,8 +66,9 @@ __global__ void selftest_kernel(double* out) {
         // RHS comparison at a generic state
         const double r = 2.2 + 60.0 * u, th = 0.05 + 3.0 * u, rs = 2.0;
         double y[8] = {1.0 + u, 0.0, 0.9 - 1.8 * u, r, 0.01 * (u - 0.3), th, 0.02 * (0.7 - u), 1.0};
-        double f[8];
-        Rhs<8>::eval(y, rs, f);
+        double kk[4] = {y[0], y[2], y[4], y[6]}, xx[4] = {y[1], y[3], y[5], y[7]}, ff[4];
+        Rhs<4>::eval(kk, xx, rs, ff);
+        double f[8] = {ff[0], 0, ff[1], 0, ff[2], 0, ff[3], 0};
         const double s = sin(th), rm = r - rs;
         const double g0 = -y[2] * y[0] * rs / (r * rm);
         const double g2 = (y[2] * y[2] * r * r * rs - y[0] * y[0] * rs * rm * rm +
@@ -70,6 +81,8 @@ __global__ void selftest_kernel(double* out) {
     atomic_max_double(&out[0], e_rcp);
     atomic_max_double(&out[1], e_root);
     atomic_max_double(&out[2], e_rhs);
+    atomic_max_double(&out[3], e_rcp3);
+    atomic_max_double(&out[4], e_sc);
 }
 
 // 16 independent DFMA chains per thread; flops = 2 * 16 * iters per thread

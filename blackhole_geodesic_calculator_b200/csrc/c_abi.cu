@@ -60,9 +60,9 @@ struct DeviceCtx {
 
 DeviceCtx g_ctx[kMaxDevices];
 
-template <int NS, bool AOS>
+template <int NK, bool AOS>
 int query_occupancy(int* out) {
-    BHG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, bhg::trace_kernel<NS, AOS>, 128, 0));
+    BHG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, bhg::trace_kernel<NK, AOS>, 128, 0));
     return 0;
 }
 
@@ -85,10 +85,10 @@ int ensure_device(int device, DeviceCtx** out) {
                         prop.major, prop.minor);
         c.sm_count = prop.multiProcessorCount;
         int rc;
-        if ((rc = query_occupancy<8, false>(&c.blocks_per_sm[0][0]))) return rc;
-        if ((rc = query_occupancy<8, true>(&c.blocks_per_sm[0][1]))) return rc;
-        if ((rc = query_occupancy<6, false>(&c.blocks_per_sm[1][0]))) return rc;
-        if ((rc = query_occupancy<6, true>(&c.blocks_per_sm[1][1]))) return rc;
+        if ((rc = query_occupancy<4, false>(&c.blocks_per_sm[0][0]))) return rc;
+        if ((rc = query_occupancy<4, true>(&c.blocks_per_sm[0][1]))) return rc;
+        if ((rc = query_occupancy<3, false>(&c.blocks_per_sm[1][0]))) return rc;
+        if ((rc = query_occupancy<3, true>(&c.blocks_per_sm[1][1]))) return rc;
         BHG_CUDA(cudaMalloc(&c.queue_slots, kQueueSlots * sizeof(unsigned long long)));
         BHG_CUDA(cudaMalloc(&c.totals, 3 * sizeof(long long)));
         c.ready = true;
@@ -139,11 +139,11 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
     long long max_blocks = (long long)c.sm_count * c.blocks_per_sm[mode][aos];
     int blocks = (int)(want_blocks < max_blocks ? want_blocks : max_blocks);
     if (mode == BHG_MODE_PARITY) {
-        if (aos) bhg::trace_kernel<8, true><<<blocks, 128, 0, stream>>>(a);
-        else bhg::trace_kernel<8, false><<<blocks, 128, 0, stream>>>(a);
+        if (aos) bhg::trace_kernel<4, true><<<blocks, 128, 0, stream>>>(a);
+        else bhg::trace_kernel<4, false><<<blocks, 128, 0, stream>>>(a);
     } else {
-        if (aos) bhg::trace_kernel<6, true><<<blocks, 128, 0, stream>>>(a);
-        else bhg::trace_kernel<6, false><<<blocks, 128, 0, stream>>>(a);
+        if (aos) bhg::trace_kernel<3, true><<<blocks, 128, 0, stream>>>(a);
+        else bhg::trace_kernel<3, false><<<blocks, 128, 0, stream>>>(a);
     }
     g_launches.fetch_add(1);
     BHG_CUDA(cudaGetLastError());
@@ -276,22 +276,22 @@ int bhg_sum_counters(const int32_t* counters_dev, const int32_t* status_dev, int
 
 int64_t bhg_launch_count(void) { return g_launches.load(); }
 
-int bhg_selftest(int32_t device, double* out4) {
+int bhg_selftest(int32_t device, double* out8) {
     DeviceCtx* c;
     int rc = ensure_device(device, &c);
     if (rc) return rc;
     double* d = nullptr;
-    BHG_CUDA(cudaMalloc(&d, 4 * sizeof(double)));
-    BHG_CUDA(cudaMemset(d, 0, 4 * sizeof(double)));
+    BHG_CUDA(cudaMalloc(&d, 8 * sizeof(double)));
+    BHG_CUDA(cudaMemset(d, 0, 8 * sizeof(double)));
     bhg::selftest_kernel<<<64, 256>>>(d);
     g_launches.fetch_add(1);
     BHG_CUDA(cudaGetLastError());
-    double h[4];
+    double h[8];
     BHG_CUDA(cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost));
     cudaFree(d);
-    if (out4) memcpy(out4, h, sizeof(h));
+    if (out8) memcpy(out8, h, sizeof(h));
     // reciprocal and tenth root to a few ulp; RHS forms agree to rounding; sincos exact by construction
-    if (!(h[0] < 1e-15) || !(h[1] < 4e-15) || !(h[2] < 1e-12)) return fail(BHG_ERR_CUDA, "selftest out of bounds: rcp %.3e root %.3e rhs %.3e", h[0], h[1], h[2]);
+    if (!(h[0] < 1e-15) || !(h[1] < 4e-15) || !(h[2] < 1e-12) || !(h[4] < 4e-16)) return fail(BHG_ERR_CUDA, "selftest out of bounds: rcp %.3e root %.3e rhs %.3e", h[0], h[1], h[2]);
     return 0;
 }
 

@@ -5,13 +5,26 @@
 //   and raytracer/LimitedRelativisticRenderEngine.py:273-278, i.e. the geodesic RHS of README.md:198-209
 //   (metric README.md:162-172, Christoffels README.md:133-135) under scipy's RK45 (README.md:196).
 // The step controller, tolerances, initial step and event semantics follow scipy 1.18.1
-// (_ivp/rk.py:8-11,14-71,85-176,538-566,715-738; _ivp/common.py:63-134; _ivp/ivp.py:52-158,659-699);
-// the arithmetic itself is organised for the FP64 pipe: one reciprocal per RHS, FMA-form stage sums,
-// Newton-refined reciprocal / inverse tenth root instead of IEEE div / pow.  Nothing here is translated
-// from the reference (it contains no solver code); the CPU restatement lives in oracle/.
+// (_ivp/rk.py:8-11,14-71,85-176,538-566,715-738; _ivp/common.py:63-134; _ivp/ivp.py:52-158,659-699).
+//
+// B200-first organisation of the same discrete algorithm:
+//  * The 8-variable system is x' = k, k' = F(x, k).  Only the four momentum derivatives K_j = F(stage j)
+//    are kept per stage; the position halves of the stage sums, of y_new, of the error estimate and of the
+//    dense output are formed from K_j with the pre-multiplied tableau products A.A, B.A, E.A, P.A
+//    (rk45_tables.cuh, exact rational arithmetic).  This is algebraically the same Dormand-Prince step as
+//    scipy's rk_step — same stages, same y_new, same error vector — but needs 28 instead of 56 doubles of
+//    stage storage, which is what lets >= 4 warps per scheduler stay resident on the FP64 pipe.
+//  * t and phi never enter the RHS, so their stage values are not formed at all (only t_new, phi_new and
+//    their error terms are).
+//  * One Newton-refined reciprocal per RHS, FMA-form sums, inverse tenth root by Newton instead of pow,
+//    sincos with table constants; all constants come from __constant__ memory (uniform loads).
+// Nothing here is translated from the reference (it contains no solver code); the CPU restatement of the
+// reference path lives in oracle/.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+
+#include "rk45_tables.cuh"
 
 namespace bhg {
 
@@ -26,33 +39,43 @@ enum Status : int {
 // lane states of the warp work queue (negative: not a final status)
 enum LaneState : int {
     LANE_RUNNING = -1,
-    LANE_PENDING_EVENT = -2,  // accepted step crossed an event surface; K, y_old, h kept for the deferred finish
     LANE_EMPTY = -4,
 };
+
+#define TAB(name) (c_tab[tab::name])
 
 // ---------------------------------------------------------------------------------------------
 // small FP64 building blocks
 // ---------------------------------------------------------------------------------------------
 
-// 1/a to ~1 ulp for normal, finite a (all call sites guarantee that or produce NaN/inf that the step
-// controller rejects): MUFU.RCP64H seed (>= 20 bits) + one third-order refinement = 3 DFMA.
+// 1/a for normal, finite a (call sites guarantee that, or produce NaN/inf that the step controller
+// rejects): MUFU.RCP64H seed, one third-order and one second-order refinement (5 DFMA).  Measured on
+// B200 against IEEE division: identical results on the self-test sweep (profiles/r1a).
 __device__ __forceinline__ double fast_rcp(double a) {
     double x0;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(a));
     double e = fma(-a, x0, 1.0);
     double e2 = fma(e, e, e);
     double x1 = fma(x0, e2, x0);
-    // one more Newton step costs 2 DFMA and makes the result independent of the seed's exact accuracy
     double e3 = fma(-a, x1, 1.0);
     return fma(x1, e3, x1);
 }
 
-// a^(-1/10) for a in [1e-12, 1e8]: float seed + two Newton steps on x^-10 = a (quadratic; 1e-6 -> 1e-22)
+// 3-DFMA variant (seed + one third-order step), used where a few ulp are irrelevant
+__device__ __forceinline__ double fast_rcp3(double a) {
+    double x0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(a));
+    double e = fma(-a, x0, 1.0);
+    double e2 = fma(e, e, e);
+    return fma(x0, e2, x0);
+}
+
+// a^(-1/10) for a in [1e-12, 1e8]: float seed + two Newton steps on x^-10 = a (quadratic; 1e-5 -> 1e-18)
 __device__ __forceinline__ double inv_tenth_root(double a) {
     float af = (float)a;
     double x = (double)exp2f(-0.1f * log2f(af));
 #pragma unroll
-    for (int i = 0; i < 3; i++) {
+    for (int i = 0; i < 2; i++) {
         double x2 = x * x;
         double x4 = x2 * x2;
         double x5 = x4 * x;
@@ -63,154 +86,226 @@ __device__ __forceinline__ double inv_tenth_root(double a) {
     return x;
 }
 
-// sin and cos of a moderate argument.  |theta| stays O(pi) on this path; the library routine's
-// Payne-Hanek slow path is kept for safety (never taken in practice, costs only a predicate).
-__device__ __forceinline__ void sincos_pi(double th, double* s, double* c) {
-    sincos(th, s, c);
+// sin and cos, < 1 ulp each: Cody-Waite reduction by pi/2 in two parts (exact for |n| < 2^20) and the
+// fdlibm kernel polynomials on [-pi/4, pi/4].  Arguments beyond 1e5 (never on this path) use the library.
+__device__ __noinline__ double2 sincos_big(double th) {  // cold path, one copy in the whole kernel
+    double2 r;
+    sincos(th, &r.x, &r.y);
+    return r;
+}
+
+__device__ __forceinline__ void sincos_tab(double th, double* s, double* c) {
+    if (!(fabs(th) < 1.0e5)) {
+        const double2 r = sincos_big(th);
+        *s = r.x;
+        *c = r.y;
+        return;
+    }
+    const int n = __double2int_rn(th * TAB(T_TWO_OVER_PI));
+    const double dn = (double)n;
+    double r = fma(-dn, TAB(T_PIO2_1), th);
+    r = fma(-dn, TAB(T_PIO2_1T), r);
+    const double z = r * r;
+    double ps = fma(z, TAB(T_S6), TAB(T_S5));
+    double pc = fma(z, TAB(T_C6), TAB(T_C5));
+    ps = fma(z, ps, TAB(T_S4));
+    pc = fma(z, pc, TAB(T_C4));
+    ps = fma(z, ps, TAB(T_S3));
+    pc = fma(z, pc, TAB(T_C3));
+    ps = fma(z, ps, TAB(T_S2));
+    pc = fma(z, pc, TAB(T_C2));
+    ps = fma(z, ps, TAB(T_S1));
+    pc = fma(z, pc, TAB(T_C1));
+    const double sr = fma(z * r, ps, r);                      // sin(r)
+    const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));      // cos(r)
+    const double a = (n & 1) ? cr : sr;
+    const double b = (n & 1) ? sr : cr;
+    // quadrant signs by flipping the sign bit with integer ops (keeps the negations off the FP64 pipe)
+    *s = __longlong_as_double(__double_as_longlong(a) ^ ((long long)(n & 2) << 62));
+    *c = __longlong_as_double(__double_as_longlong(b) ^ ((long long)((n + 1) & 2) << 62));
 }
 
 // ---------------------------------------------------------------------------------------------
-// RK45 (Dormand-Prince) tableau, scipy/_ivp/rk.py:538-566
+// right-hand sides: momentum derivatives only (positions' derivatives are the momenta themselves).
+//   NK = 4 (parity): k = (k_t, k_r, k_th, k_ph), x = (t, r, th, ph)
+//   NK = 3 (plane) : k = (k_t, k_r, k_ph),       x = (t, r, ph)      (theta = pi/2, k_th = 0)
 // ---------------------------------------------------------------------------------------------
-#define BHG_A21 (1.0 / 5)
-#define BHG_A31 (3.0 / 40)
-#define BHG_A32 (9.0 / 40)
-#define BHG_A41 (44.0 / 45)
-#define BHG_A42 (-56.0 / 15)
-#define BHG_A43 (32.0 / 9)
-#define BHG_A51 (19372.0 / 6561)
-#define BHG_A52 (-25360.0 / 2187)
-#define BHG_A53 (64448.0 / 6561)
-#define BHG_A54 (-212.0 / 729)
-#define BHG_A61 (9017.0 / 3168)
-#define BHG_A62 (-355.0 / 33)
-#define BHG_A63 (46732.0 / 5247)
-#define BHG_A64 (49.0 / 176)
-#define BHG_A65 (-5103.0 / 18656)
-#define BHG_B1 (35.0 / 384)
-#define BHG_B3 (500.0 / 1113)
-#define BHG_B4 (125.0 / 192)
-#define BHG_B5 (-2187.0 / 6784)
-#define BHG_B6 (11.0 / 84)
-#define BHG_E1 (-71.0 / 57600)
-#define BHG_E3 (71.0 / 16695)
-#define BHG_E4 (-71.0 / 1920)
-#define BHG_E5 (17253.0 / 339200)
-#define BHG_E6 (-22.0 / 525)
-#define BHG_E7 (1.0 / 40)
-
-// ---------------------------------------------------------------------------------------------
-// right-hand sides.  State order [k_t, t, k_r, r, k_th, th, k_ph, ph] (parity, NS=8) and
-// [k_t, t, k_r, r, k_ph, ph] (orbital plane theta=pi/2, NS=6).
-// ---------------------------------------------------------------------------------------------
-template <int NS>
+template <int NK>
 struct Rhs;
 
 template <>
-struct Rhs<8> {
-    static constexpr int IR = 3;
-    __device__ __forceinline__ static void eval(const double (&y)[8], double rs, double (&f)[8]) {
-        const double kt = y[0], kr = y[2], r = y[3], kth = y[4], th = y[5], kph = y[6];
+struct Rhs<4> {
+    // which position components the RHS reads (r and theta): only those get stage values
+    __device__ __forceinline__ static constexpr bool needs_x(int i) { return i == 1 || i == 2; }
+    __device__ __forceinline__ static void eval(const double (&k)[4], const double (&x)[4], double rs,
+                                                double (&f)[4]) {
+        const double kt = k[0], kr = k[1], kth = k[2], kph = k[3], r = x[1], th = x[2];
         double s, c;
-        sincos_pi(th, &s, &c);
+        sincos_tab(th, &s, &c);
         const double rm = r - rs;
-        // the only two reciprocals of the RHS; independent of each other so they overlap in the pipe
-        const double i_rrm = fast_rcp(r * rm);  // 1 / (r (r - rs))
-        const double i_s = fast_rcp(s);         // 1 / sin(theta)
-        const double i_r = i_rrm * rm;          // 1 / r
-        const double A = rs * i_rrm;            // rs / (r (r - rs))
-        const double kph2 = kph * kph;
-        const double ang = fma(kph2 * s, s, kth * kth);  // k_th^2 + k_ph^2 sin^2
+        const double p = r * rm;
+        const double inv = fast_rcp(p * s);   // 1 / (r (r - rs) sin th): the only reciprocal
+        const double i_s = inv * p;           // 1 / sin th
+        const double i_rrm = inv * s;         // 1 / (r (r - rs))
+        const double i_r = i_rrm * rm;        // 1 / r
+        const double A = rs * i_rrm;          // rs / (r (r - rs))
+        const double hA = 0.5 * A;
+        const double kph2s = (kph * kph) * s;
+        const double ang = fma(kph2s, s, kth * kth);  // k_th^2 + k_ph^2 sin^2
+        const double q = rm * i_r;                    // (r - rs) / r
+        const double w = (hA * q) * q;                // rs (r - rs) / (2 r^3)
+        const double kr_r = kr * i_r;
         f[0] = -(A * kr) * kt;
-        f[1] = kt;
-        // (rs/(2 r rm)) kr^2 - (rs rm/(2 r^3)) kt^2 + rm * ang
-        const double half_A = 0.5 * A;
-        const double w = (half_A * rm) * (rm * i_r) * i_r;  // rs rm / (2 r^3) = half_A * rm^2 / r^2
-        f[2] = fma(half_A * kr, kr, fma(-w * kt, kt, rm * ang));
-        f[3] = kr;
-        f[4] = fma(kph2 * s, c, -2.0 * (kr * i_r) * kth);
-        f[5] = kth;
-        f[6] = -2.0 * kph * fma(kr, i_r, kth * (c * i_s));
-        f[7] = kph;
+        f[1] = fma(hA * kr, kr, fma(-w * kt, kt, rm * ang));
+        f[2] = fma(kph2s, c, -2.0 * (kr_r * kth));
+        f[3] = -2.0 * kph * fma(kth, c * i_s, kr_r);
     }
 };
 
 template <>
-struct Rhs<6> {
-    static constexpr int IR = 3;
-    __device__ __forceinline__ static void eval(const double (&y)[6], double rs, double (&f)[6]) {
-        const double kt = y[0], kr = y[2], r = y[3], kph = y[4];
+struct Rhs<3> {
+    __device__ __forceinline__ static constexpr bool needs_x(int i) { return i == 1; }
+    __device__ __forceinline__ static void eval(const double (&k)[3], const double (&x)[3], double rs,
+                                                double (&f)[3]) {
+        const double kt = k[0], kr = k[1], kph = k[2], r = x[1];
         const double rm = r - rs;
         const double i_rrm = fast_rcp(r * rm);
         const double i_r = i_rrm * rm;
         const double A = rs * i_rrm;
-        const double half_A = 0.5 * A;
-        const double w = (half_A * rm) * (rm * i_r) * i_r;
+        const double hA = 0.5 * A;
+        const double q = rm * i_r;
+        const double w = (hA * q) * q;
         f[0] = -(A * kr) * kt;
-        f[1] = kt;
-        f[2] = fma(half_A * kr, kr, fma(-w * kt, kt, rm * (kph * kph)));
-        f[3] = kr;
-        f[4] = -2.0 * kph * (kr * i_r);
-        f[5] = kph;
+        f[1] = fma(hA * kr, kr, fma(-w * kt, kt, rm * (kph * kph)));
+        f[2] = -2.0 * kph * (kr * i_r);
     }
 };
 
 // ---------------------------------------------------------------------------------------------
-// one RK45 attempt (rk_step + error estimate, scipy/_ivp/rk.py:14-71,105-109,143-146).
-// On entry K[0] = f(y).  Fills K[1..6], yn; returns sum_i (err_i / scale_i)^2.
+// one RK45 attempt in Nystrom form (rk_step + error estimate, scipy/_ivp/rk.py:14-71,105-109,143-146).
+// On entry K[0] = F(k, x).  Fills K[1..6], kn, xn; returns sum_i (err_i / scale_i)^2 over all 2 NK
+// components of the state.
 // ---------------------------------------------------------------------------------------------
-template <int NS>
-__device__ __forceinline__ double ynew_component(const double yi, const double k0, const double k2, const double k3,
-                                                 const double k4, const double k5, const double h) {
-    double acc = BHG_B1 * k0;
-    acc = fma(BHG_B3, k2, acc);
-    acc = fma(BHG_B4, k3, acc);
-    acc = fma(BHG_B5, k4, acc);
-    acc = fma(BHG_B6, k5, acc);
-    return fma(h, acc, yi);
+template <int NK>
+__device__ __forceinline__ double knew_component(double ki, double K0, double K2, double K3, double K4, double K5,
+                                                 double h) {
+    double acc = TAB(B1) * K0;
+    acc = fma(TAB(B3), K2, acc);
+    acc = fma(TAB(B4), K3, acc);
+    acc = fma(TAB(B5), K4, acc);
+    acc = fma(TAB(B6), K5, acc);
+    return fma(h, acc, ki);
 }
 
-template <int NS>
-__device__ __forceinline__ double rk45_attempt(const double (&y)[NS], double (&K)[7][NS], double (&yn)[NS],
-                                               const double h, const double rs, const double rtol,
-                                               const double atol) {
-    double yt[NS];
+template <int NK>
+__device__ __forceinline__ double xnew_component(double xi, double ki, double K0, double K1, double K2, double K3,
+                                                 double K4, double h, double h2) {
+    double acc = TAB(BA1) * K0;
+    acc = fma(TAB(BA2), K1, acc);
+    acc = fma(TAB(BA3), K2, acc);
+    acc = fma(TAB(BA4), K3, acc);
+    acc = fma(TAB(BA5), K4, acc);
+    return fma(h2, acc, fma(h, ki, xi));
+}
+
+template <int NK>
+__device__ __forceinline__ double rk45_attempt(const double (&k)[NK], const double (&x)[NK], double (&K)[7][NK],
+                                               double (&kn)[NK], double (&xn)[NK], const double h, const double rs,
+                                               const double rtol, const double atol) {
+    const double h2 = h * h;
+    double kt[NK], xt[NK];
 #pragma unroll
-    for (int i = 0; i < NS; i++) yt[i] = fma(h * BHG_A21, K[0][i], y[i]);
-    Rhs<NS>::eval(yt, rs, K[1]);
+    for (int i = 0; i < NK; i++) xt[i] = x[i];
+    // ---- stage 2
+    {
+        const double ha = h * TAB(A21), hc = h * TAB(C2);
 #pragma unroll
-    for (int i = 0; i < NS; i++) yt[i] = fma(h, fma(BHG_A32, K[1][i], BHG_A31 * K[0][i]), y[i]);
-    Rhs<NS>::eval(yt, rs, K[2]);
+        for (int i = 0; i < NK; i++) {
+            kt[i] = fma(ha, K[0][i], k[i]);
+            if (Rhs<NK>::needs_x(i)) xt[i] = fma(hc, k[i], x[i]);
+        }
+        Rhs<NK>::eval(kt, xt, rs, K[1]);
+    }
+    // ---- stage 3
+    {
+        const double hc = h * TAB(C3);
 #pragma unroll
-    for (int i = 0; i < NS; i++)
-        yt[i] = fma(h, fma(BHG_A43, K[2][i], fma(BHG_A42, K[1][i], BHG_A41 * K[0][i])), y[i]);
-    Rhs<NS>::eval(yt, rs, K[3]);
+        for (int i = 0; i < NK; i++) {
+            kt[i] = fma(h, fma(TAB(A32), K[1][i], TAB(A31) * K[0][i]), k[i]);
+            if (Rhs<NK>::needs_x(i)) xt[i] = fma(h2, TAB(AA31) * K[0][i], fma(hc, k[i], x[i]));
+        }
+        Rhs<NK>::eval(kt, xt, rs, K[2]);
+    }
+    // ---- stage 4
+    {
+        const double hc = h * TAB(C4);
 #pragma unroll
-    for (int i = 0; i < NS; i++)
-        yt[i] = fma(h, fma(BHG_A54, K[3][i], fma(BHG_A53, K[2][i], fma(BHG_A52, K[1][i], BHG_A51 * K[0][i]))), y[i]);
-    Rhs<NS>::eval(yt, rs, K[4]);
+        for (int i = 0; i < NK; i++) {
+            kt[i] = fma(h, fma(TAB(A43), K[2][i], fma(TAB(A42), K[1][i], TAB(A41) * K[0][i])), k[i]);
+            if (Rhs<NK>::needs_x(i))
+                xt[i] = fma(h2, fma(TAB(AA42), K[1][i], TAB(AA41) * K[0][i]), fma(hc, k[i], x[i]));
+        }
+        Rhs<NK>::eval(kt, xt, rs, K[3]);
+    }
+    // ---- stage 5
+    {
+        const double hc = h * TAB(C5);
 #pragma unroll
-    for (int i = 0; i < NS; i++)
-        yt[i] = fma(h,
-                    fma(BHG_A65, K[4][i],
-                        fma(BHG_A64, K[3][i], fma(BHG_A63, K[2][i], fma(BHG_A62, K[1][i], BHG_A61 * K[0][i])))),
-                    y[i]);
-    Rhs<NS>::eval(yt, rs, K[5]);
+        for (int i = 0; i < NK; i++) {
+            kt[i] = fma(h, fma(TAB(A54), K[3][i], fma(TAB(A53), K[2][i], fma(TAB(A52), K[1][i], TAB(A51) * K[0][i]))),
+                        k[i]);
+            if (Rhs<NK>::needs_x(i))
+                xt[i] = fma(h2, fma(TAB(AA53), K[2][i], fma(TAB(AA52), K[1][i], TAB(AA51) * K[0][i])),
+                            fma(hc, k[i], x[i]));
+        }
+        Rhs<NK>::eval(kt, xt, rs, K[4]);
+    }
+    // ---- stage 6 (c6 = 1)
+    {
 #pragma unroll
-    for (int i = 0; i < NS; i++) yn[i] = ynew_component<NS>(y[i], K[0][i], K[2][i], K[3][i], K[4][i], K[5][i], h);
-    Rhs<NS>::eval(yn, rs, K[6]);
+        for (int i = 0; i < NK; i++) {
+            kt[i] = fma(h,
+                        fma(TAB(A65), K[4][i],
+                            fma(TAB(A64), K[3][i], fma(TAB(A63), K[2][i], fma(TAB(A62), K[1][i], TAB(A61) * K[0][i])))),
+                        k[i]);
+            if (Rhs<NK>::needs_x(i))
+                xt[i] = fma(h2,
+                            fma(TAB(AA64), K[3][i], fma(TAB(AA63), K[2][i], fma(TAB(AA62), K[1][i], TAB(AA61) * K[0][i]))),
+                            fma(h, k[i], x[i]));
+        }
+        Rhs<NK>::eval(kt, xt, rs, K[5]);
+    }
+    // ---- new state and FSAL stage
+#pragma unroll
+    for (int i = 0; i < NK; i++) {
+        kn[i] = knew_component<NK>(k[i], K[0][i], K[2][i], K[3][i], K[4][i], K[5][i], h);
+        xn[i] = xnew_component<NK>(x[i], k[i], K[0][i], K[1][i], K[2][i], K[3][i], K[4][i], h, h2);
+    }
+    Rhs<NK>::eval(kn, xn, rs, K[6]);
+    // ---- error estimate, scaled (rk.py:143-146, common.py:63-65)
     double esum = 0.0;
 #pragma unroll
-    for (int i = 0; i < NS; i++) {
-        double e = BHG_E1 * K[0][i];
-        e = fma(BHG_E3, K[2][i], e);
-        e = fma(BHG_E4, K[3][i], e);
-        e = fma(BHG_E5, K[4][i], e);
-        e = fma(BHG_E6, K[5][i], e);
-        e = fma(BHG_E7, K[6][i], e);
-        const double scale = fma(fmax(fabs(y[i]), fabs(yn[i])), rtol, atol);
-        const double q = (e * h) * fast_rcp(scale);
-        esum = fma(q, q, esum);
+    for (int i = 0; i < NK; i++) {
+        double ek = TAB(E1) * K[0][i];
+        ek = fma(TAB(E3), K[2][i], ek);
+        ek = fma(TAB(E4), K[3][i], ek);
+        ek = fma(TAB(E5), K[4][i], ek);
+        ek = fma(TAB(E6), K[5][i], ek);
+        ek = fma(TAB(E7), K[6][i], ek);
+        double ex = TAB(EA1) * K[0][i];
+        ex = fma(TAB(EA2), K[1][i], ex);
+        ex = fma(TAB(EA3), K[2][i], ex);
+        ex = fma(TAB(EA4), K[3][i], ex);
+        ex = fma(TAB(EA5), K[4][i], ex);
+        ex = fma(TAB(EA6), K[5][i], ex);
+        const double sk = fma(fmax(fabs(k[i]), fabs(kn[i])), rtol, atol);
+        const double sx = fma(fmax(fabs(x[i]), fabs(xn[i])), rtol, atol);
+        // one reciprocal for the pair
+        const double inv = fast_rcp(sk * sx);
+        const double qk = (ek * h) * (inv * sx);
+        const double qx = (ex * h2) * (inv * sk);
+        esum = fma(qk, qk, esum);
+        esum = fma(qx, qx, esum);
     }
     return esum;
 }
@@ -231,35 +326,43 @@ __device__ __forceinline__ double min_step_at(double t) {
 
 // ---------------------------------------------------------------------------------------------
 // Hairer's initial step (scipy/_ivp/common.py:109-134, order = 4, direction = +1); one RHS evaluation.
+// f0 = (K0, k) in the (momentum, position) split.
 // ---------------------------------------------------------------------------------------------
-template <int NS>
-__device__ __forceinline__ double initial_step(const double (&y)[NS], const double (&f0)[NS], double rs, double rtol,
-                                               double atol, double interval, double max_step) {
+template <int NK>
+__device__ __forceinline__ double initial_step(const double (&k)[NK], const double (&x)[NK], const double (&K0)[NK],
+                                               double rs, double rtol, double atol, double interval,
+                                               double max_step) {
     if (interval == 0.0) return 0.0;
-    double iscale[NS];
+    double isk[NK], isx[NK];
     double d0 = 0.0, d1 = 0.0;
 #pragma unroll
-    for (int i = 0; i < NS; i++) {
-        iscale[i] = 1.0 / fma(fabs(y[i]), rtol, atol);
-        const double a = y[i] * iscale[i], b = f0[i] * iscale[i];
-        d0 = fma(a, a, d0);
-        d1 = fma(b, b, d1);
+    for (int i = 0; i < NK; i++) {
+        isk[i] = 1.0 / fma(fabs(k[i]), rtol, atol);
+        isx[i] = 1.0 / fma(fabs(x[i]), rtol, atol);
+        const double a = k[i] * isk[i], b = x[i] * isx[i];
+        const double c = K0[i] * isk[i], d = k[i] * isx[i];
+        d0 = fma(a, a, fma(b, b, d0));
+        d1 = fma(c, c, fma(d, d, d1));
     }
-    d0 = sqrt(d0 / NS);
-    d1 = sqrt(d1 / NS);
+    d0 = sqrt(d0 / (2 * NK));
+    d1 = sqrt(d1 / (2 * NK));
     double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
     h0 = fmin(h0, interval);
-    double y1[NS], f1[NS];
+    double k1[NK], x1[NK], F1[NK];
 #pragma unroll
-    for (int i = 0; i < NS; i++) y1[i] = fma(h0, f0[i], y[i]);
-    Rhs<NS>::eval(y1, rs, f1);
+    for (int i = 0; i < NK; i++) {
+        k1[i] = fma(h0, K0[i], k[i]);
+        x1[i] = fma(h0, k[i], x[i]);
+    }
+    Rhs<NK>::eval(k1, x1, rs, F1);
     double d2 = 0.0;
 #pragma unroll
-    for (int i = 0; i < NS; i++) {
-        const double a = (f1[i] - f0[i]) * iscale[i];
-        d2 = fma(a, a, d2);
+    for (int i = 0; i < NK; i++) {
+        const double a = (F1[i] - K0[i]) * isk[i];
+        const double b = (k1[i] - k[i]) * isx[i];
+        d2 = fma(a, a, fma(b, b, d2));
     }
-    d2 = sqrt(d2 / NS) / h0;
+    d2 = sqrt(d2 / (2 * NK)) / h0;
     double h1;
     if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
     else h1 = pow(0.01 / fmax(d1, d2), 0.2);
@@ -267,45 +370,40 @@ __device__ __forceinline__ double initial_step(const double (&y)[NS], const doub
 }
 
 // ---------------------------------------------------------------------------------------------
-// dense output (scipy/_ivp/rk.py:554-566,715-738): y(t_old + x h) = y_old + h * sum_c Q_c x^(c+1)
+// dense output (scipy/_ivp/rk.py:554-566,715-738): y(t_old + s h) = y_old + h * sum_c Q_c s^(c+1)
+//   momentum: Q_c = sum_j K_j P[j][c]
+//   position: Q_c = k PS[c] + h sum_l K_l PA[l][c]
 // ---------------------------------------------------------------------------------------------
-#define BHG_P11 (-8048581381.0 / 2820520608)
-#define BHG_P12 (8663915743.0 / 2820520608)
-#define BHG_P13 (-12715105075.0 / 11282082432)
-#define BHG_P31 (131558114200.0 / 32700410799)
-#define BHG_P32 (-68118460800.0 / 10900136933)
-#define BHG_P33 (87487479700.0 / 32700410799)
-#define BHG_P41 (-1754552775.0 / 470086768)
-#define BHG_P42 (14199869525.0 / 1410260304)
-#define BHG_P43 (-10690763975.0 / 1880347072)
-#define BHG_P51 (127303824393.0 / 49829197408)
-#define BHG_P52 (-318862633887.0 / 49829197408)
-#define BHG_P53 (701980252875.0 / 199316789632)
-#define BHG_P61 (-282668133.0 / 205662961)
-#define BHG_P62 (2019193451.0 / 616988883)
-#define BHG_P63 (-1453857185.0 / 822651844)
-#define BHG_P71 (40617522.0 / 29380423)
-#define BHG_P72 (-110615467.0 / 29380423)
-#define BHG_P73 (69997945.0 / 29380423)
-
-__device__ __forceinline__ void dense_coeffs(double k0, double k2, double k3, double k4, double k5, double k6,
-                                             double (&q)[4]) {
-    q[0] = k0;
-    q[1] = fma(BHG_P71, k6, fma(BHG_P61, k5, fma(BHG_P51, k4, fma(BHG_P41, k3, fma(BHG_P31, k2, BHG_P11 * k0)))));
-    q[2] = fma(BHG_P72, k6, fma(BHG_P62, k5, fma(BHG_P52, k4, fma(BHG_P42, k3, fma(BHG_P32, k2, BHG_P12 * k0)))));
-    q[3] = fma(BHG_P73, k6, fma(BHG_P63, k5, fma(BHG_P53, k4, fma(BHG_P43, k3, fma(BHG_P33, k2, BHG_P13 * k0)))));
+__device__ __forceinline__ void dense_coeffs_k(double K0, double K2, double K3, double K4, double K5, double K6,
+                                               double (&q)[4]) {
+    q[0] = K0;
+    q[1] = fma(TAB(P71), K6, fma(TAB(P61), K5, fma(TAB(P51), K4, fma(TAB(P41), K3, fma(TAB(P31), K2, TAB(P11) * K0)))));
+    q[2] = fma(TAB(P72), K6, fma(TAB(P62), K5, fma(TAB(P52), K4, fma(TAB(P42), K3, fma(TAB(P32), K2, TAB(P12) * K0)))));
+    q[3] = fma(TAB(P73), K6, fma(TAB(P63), K5, fma(TAB(P53), K4, fma(TAB(P43), K3, fma(TAB(P33), K2, TAB(P13) * K0)))));
 }
 
-__device__ __forceinline__ double dense_eval(const double (&q)[4], double yold, double h, double x) {
-    // same term order as numpy: p = cumprod([x,x,x,x]); y = h * dot(Q, p) + y_old
-    const double p2 = x * x, p3 = p2 * x, p4 = p3 * x;
-    const double acc = fma(q[3], p4, fma(q[2], p3, fma(q[1], p2, q[0] * x)));
+__device__ __forceinline__ void dense_coeffs_x(double ki, double K0, double K1, double K2, double K3, double K4,
+                                               double K5, double h, double (&q)[4]) {
+    const double s0 = fma(TAB(PA60), K5, fma(TAB(PA50), K4, fma(TAB(PA40), K3, fma(TAB(PA30), K2, fma(TAB(PA20), K1, TAB(PA10) * K0)))));
+    const double s1 = fma(TAB(PA61), K5, fma(TAB(PA51), K4, fma(TAB(PA41), K3, fma(TAB(PA31), K2, fma(TAB(PA21), K1, TAB(PA11) * K0)))));
+    const double s2 = fma(TAB(PA62), K5, fma(TAB(PA52), K4, fma(TAB(PA42), K3, fma(TAB(PA32), K2, fma(TAB(PA22), K1, TAB(PA12) * K0)))));
+    const double s3 = fma(TAB(PA63), K5, fma(TAB(PA53), K4, fma(TAB(PA43), K3, fma(TAB(PA33), K2, fma(TAB(PA23), K1, TAB(PA13) * K0)))));
+    q[0] = fma(h, s0, ki);  // PS[0] = 1
+    q[1] = fma(h, s1, TAB(PS1) * ki);
+    q[2] = fma(h, s2, TAB(PS2) * ki);
+    q[3] = fma(h, s3, TAB(PS3) * ki);
+}
+
+__device__ __forceinline__ double dense_eval(const double (&q)[4], double yold, double h, double s) {
+    // same term order as numpy: p = cumprod([s,s,s,s]); y = h * dot(Q, p) + y_old
+    const double p2 = s * s, p3 = p2 * s, p4 = p3 * s;
+    const double acc = fma(q[3], p4, fma(q[2], p3, fma(q[1], p2, q[0] * s)));
     return fma(h, acc, yold);
 }
 
-// Root of r(x) - target on x in [0,1] given a sign change between the end points.
+// Root of r(s) - target on s in [0,1] given a sign change between the end points.
 // scipy uses brentq(xtol=rtol=4 eps) on the same quartic (ivp.py:52-77); any bracketing method that
-// converges to the last bit of x lands inside brentq's own tolerance.  Newton with bisection safeguard.
+// converges to the last bit of s lands inside brentq's own tolerance.  Newton with bisection safeguard.
 __device__ __forceinline__ double event_root(const double (&q)[4], double rold, double h, double target) {
     double lo = 0.0, hi = 1.0;
     double flo = rold - target;
@@ -313,20 +411,19 @@ __device__ __forceinline__ double event_root(const double (&q)[4], double rold, 
     if (flo == 0.0) return 0.0;
     if (fhi == 0.0) return 1.0;
     const bool lo_neg = flo < 0.0;
-    double x = flo / (flo - fhi);  // secant start
-    if (!(x > 0.0 && x < 1.0)) x = 0.5;
+    double s = flo / (flo - fhi);  // secant start
+    if (!(s > 0.0 && s < 1.0)) s = 0.5;
     for (int it = 0; it < 80; it++) {
-        const double fx = dense_eval(q, rold, h, x) - target;
-        if (fx == 0.0) return x;
-        if ((fx < 0.0) == lo_neg) lo = x; else hi = x;
-        // derivative of h * (q0 x + q1 x^2 + q2 x^3 + q3 x^4)
-        const double dfx = h * fma(4.0 * q[3], x * x * x, fma(3.0 * q[2], x * x, fma(2.0 * q[1], x, q[0])));
-        double xn = x - fx / dfx;
-        if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
-        if (fabs(xn - x) <= 2.220446049250313e-16 * fmax(fabs(xn), 1e-3) || hi - lo <= 4.4e-16 * hi) return xn;
-        x = xn;
+        const double fs = dense_eval(q, rold, h, s) - target;
+        if (fs == 0.0) return s;
+        if ((fs < 0.0) == lo_neg) lo = s; else hi = s;
+        const double dfs = h * fma(4.0 * q[3], s * s * s, fma(3.0 * q[2], s * s, fma(2.0 * q[1], s, q[0])));
+        double sn = s - fs / dfs;
+        if (!(sn > lo && sn < hi)) sn = 0.5 * (lo + hi);
+        if (fabs(sn - s) <= 2.220446049250313e-16 * fmax(fabs(sn), 1e-3) || hi - lo <= 4.4e-16 * hi) return sn;
+        s = sn;
     }
-    return x;
+    return s;
 }
 
 }  // namespace bhg

@@ -80,42 +80,43 @@ __device__ __forceinline__ void store_ray(const TraceArgs& a, long long idx, con
 
 // ---- entry conversion (RelativisticRenderEngine.py:289-291: Conversions().convert_xyz_to_sph) -----------
 // returns false when the ray starts at or inside the capture surface
-template <int NS>
-__device__ __forceinline__ bool init_state(const double (&x)[3], const double (&k)[3], double rs, double r_hor,
-                                           double (&y)[NS]);
+template <int NK>
+__device__ __forceinline__ bool init_state(const double (&x0)[3], const double (&k0)[3], double rs, double r_hor,
+                                           double (&k)[NK], double (&x)[NK]);
 
 template <>
-__device__ __forceinline__ bool init_state<8>(const double (&x)[3], const double (&k)[3], double rs, double r_hor,
-                                              double (&y)[8]) {
-    const double rho2 = fma(x[0], x[0], x[1] * x[1]);
-    const double r2 = fma(x[2], x[2], rho2);
+__device__ __forceinline__ bool init_state<4>(const double (&x0)[3], const double (&k0)[3], double rs, double r_hor,
+                                              double (&k)[4], double (&x)[4]) {
+    const double rho2 = fma(x0[0], x0[0], x0[1] * x0[1]);
+    const double r2 = fma(x0[2], x0[2], rho2);
     const double r = sqrt(r2), rho = sqrt(rho2);
     if (!(r > r_hor)) return false;
-    const double th = acos(x[2] / r);
-    const double ph = atan2(x[1], x[0]);
-    const double xk = fma(x[0], k[0], x[1] * k[1]);
-    const double k_r = fma(x[2], k[2], xk) / r;
-    const double k_th = fma(x[2], xk, -rho2 * k[2]) / (r2 * rho);
-    const double k_ph = fma(x[0], k[1], -x[1] * k[0]) / rho2;
+    const double th = acos(x0[2] / r);
+    const double ph = atan2(x0[1], x0[0]);
+    const double xk = fma(x0[0], k0[0], x0[1] * k0[1]);
+    const double k_r = fma(x0[2], k0[2], xk) / r;
+    const double k_th = fma(x0[2], xk, -rho2 * k0[2]) / (r2 * rho);
+    const double k_ph = fma(x0[0], k0[1], -x0[1] * k0[0]) / rho2;
     const double s = sin(th);
     const double rm = r - rs;
     // null condition g_mn k^m k^n = 0, future-directed root (time_like=False, RelativisticRenderEngine.py:134)
     const double k_t = r * sqrt(fma(k_r, k_r, rm * r * fma(k_ph * k_ph * s, s, k_th * k_th))) / rm;
-    y[0] = k_t; y[1] = 0.0; y[2] = k_r; y[3] = r; y[4] = k_th; y[5] = th; y[6] = k_ph; y[7] = ph;
+    k[0] = k_t; k[1] = k_r; k[2] = k_th; k[3] = k_ph;
+    x[0] = 0.0; x[1] = r; x[2] = th; x[3] = ph;
     return true;
 }
 
 // orbital-plane frame: e1 = x/|x|, e2 = unit(k - (k.e1) e1); phi measured from e1 inside the plane
-__device__ __forceinline__ void plane_frame(const double (&x)[3], const double (&k)[3], double& r, double& k_r,
+__device__ __forceinline__ void plane_frame(const double (&x0)[3], const double (&k0)[3], double& r, double& k_r,
                                             double& wn, double (&e1)[3], double (&e2)[3]) {
-    r = sqrt(fma(x[0], x[0], fma(x[1], x[1], x[2] * x[2])));
+    r = sqrt(fma(x0[0], x0[0], fma(x0[1], x0[1], x0[2] * x0[2])));
     const double ir = 1.0 / r;
 #pragma unroll
-    for (int c = 0; c < 3; c++) e1[c] = x[c] * ir;
-    k_r = fma(k[0], e1[0], fma(k[1], e1[1], k[2] * e1[2]));
+    for (int c = 0; c < 3; c++) e1[c] = x0[c] * ir;
+    k_r = fma(k0[0], e1[0], fma(k0[1], e1[1], k0[2] * e1[2]));
     double w[3];
 #pragma unroll
-    for (int c = 0; c < 3; c++) w[c] = fma(-k_r, e1[c], k[c]);
+    for (int c = 0; c < 3; c++) w[c] = fma(-k_r, e1[c], k0[c]);
     wn = sqrt(fma(w[0], w[0], fma(w[1], w[1], w[2] * w[2])));
     const double iw = wn > 0.0 ? 1.0 / wn : 0.0;
 #pragma unroll
@@ -123,30 +124,31 @@ __device__ __forceinline__ void plane_frame(const double (&x)[3], const double (
 }
 
 template <>
-__device__ __forceinline__ bool init_state<6>(const double (&x)[3], const double (&k)[3], double rs, double r_hor,
-                                              double (&y)[6]) {
+__device__ __forceinline__ bool init_state<3>(const double (&x0)[3], const double (&k0)[3], double rs, double r_hor,
+                                              double (&k)[3], double (&x)[3]) {
     double r, k_r, wn, e1[3], e2[3];
-    plane_frame(x, k, r, k_r, wn, e1, e2);
+    plane_frame(x0, k0, r, k_r, wn, e1, e2);
     if (!(r > r_hor)) return false;
     const double k_ph = wn / r;
     const double rm = r - rs;
     const double k_t = r * sqrt(fma(k_r, k_r, rm * r * (k_ph * k_ph))) / rm;
-    y[0] = k_t; y[1] = 0.0; y[2] = k_r; y[3] = r; y[4] = k_ph; y[5] = 0.0;
+    k[0] = k_t; k[1] = k_r; k[2] = k_ph;
+    x[0] = 0.0; x[1] = r; x[2] = 0.0;
     return true;
 }
 
 // ---- exit conversion: spherical state -> Cartesian position + unit direction ----------------------------
-template <int NS>
-__device__ __forceinline__ void exit_state(const double (&y)[NS], const double (&x0)[3], const double (&k0)[3],
-                                           double (&xo)[3], double (&ko)[3]);
+template <int NK>
+__device__ __forceinline__ void exit_state(const double (&k)[NK], const double (&x)[NK], const double (&x0)[3],
+                                           const double (&k0)[3], double (&xo)[3], double (&ko)[3]);
 
 template <>
-__device__ __forceinline__ void exit_state<8>(const double (&y)[8], const double (&)[3], const double (&)[3],
-                                              double (&xo)[3], double (&ko)[3]) {
+__device__ __forceinline__ void exit_state<4>(const double (&k)[4], const double (&x)[4], const double (&)[3],
+                                              const double (&)[3], double (&xo)[3], double (&ko)[3]) {
     double st, ct, sp, cp;
-    sincos(y[5], &st, &ct);
-    sincos(y[7], &sp, &cp);
-    const double R = y[3], k_r = y[2], k_th = y[4], k_ph = y[6];
+    sincos(x[2], &st, &ct);
+    sincos(x[3], &sp, &cp);
+    const double R = x[1], k_r = k[1], k_th = k[2], k_ph = k[3];
     xo[0] = R * st * cp;
     xo[1] = R * st * sp;
     xo[2] = R * ct;
@@ -162,15 +164,15 @@ __device__ __forceinline__ void exit_state<8>(const double (&y)[8], const double
 }
 
 template <>
-__device__ __forceinline__ void exit_state<6>(const double (&y)[6], const double (&x0)[3], const double (&k0)[3],
-                                              double (&xo)[3], double (&ko)[3]) {
+__device__ __forceinline__ void exit_state<3>(const double (&k)[3], const double (&x)[3], const double (&x0)[3],
+                                              const double (&k0)[3], double (&xo)[3], double (&ko)[3]) {
     double r0, kr0, wn, e1[3], e2[3];
     plane_frame(x0, k0, r0, kr0, wn, e1, e2);
     double sp, cp;
-    sincos(y[5], &sp, &cp);
-    const double R = y[3];
-    const double a = fma(y[2], cp, -R * sp * y[4]);
-    const double b = fma(y[2], sp, R * cp * y[4]);
+    sincos(x[2], &sp, &cp);
+    const double R = x[1];
+    const double a = fma(k[1], cp, -R * sp * k[2]);
+    const double b = fma(k[1], sp, R * cp * k[2]);
     const double inv = 1.0 / sqrt(fma(a, a, b * b));
 #pragma unroll
     for (int c = 0; c < 3; c++) {
@@ -179,22 +181,26 @@ __device__ __forceinline__ void exit_state<6>(const double (&y)[6], const double
     }
 }
 
-template <int NS>
-__device__ __forceinline__ bool all_finite(const double (&y)[NS]) {
+template <int NK>
+__device__ __forceinline__ bool all_finite(const double (&k)[NK], const double (&x)[NK]) {
     bool ok = true;
 #pragma unroll
-    for (int i = 0; i < NS; i++) ok = ok && isfinite(y[i]);
+    for (int i = 0; i < NK; i++) ok = ok && isfinite(k[i]) && isfinite(x[i]);
     return ok;
 }
 
-template <int NS, bool AOS>
-__global__ void __launch_bounds__(128) trace_kernel(const TraceArgs a) {
-    constexpr int IR = Rhs<NS>::IR;
+#ifndef BHG_MIN_BLOCKS
+#define BHG_MIN_BLOCKS 4
+#endif
+
+template <int NK, bool AOS>
+__global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceArgs a) {
+    constexpr int IR = 1;  // index of r in x
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    double y[NS], K[7][NS], yn[NS];
+    double k[NK], x[NK], K[7][NK], kn[NK], xn[NK];
     double t = 0.0, h_abs = 0.0;
     long long idx = -1;
     int state = LANE_EMPTY;
@@ -205,9 +211,8 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceArgs a) {
     const double t_bound = a.lambda_max;
 
 #pragma unroll
-    for (int i = 0; i < NS; i++) {
-        y[i] = 0.0;
-        yn[i] = 0.0;
+    for (int i = 0; i < NK; i++) {
+        k[i] = x[i] = kn[i] = xn[i] = 0.0;
 #pragma unroll
         for (int s = 0; s < 7; s++) K[s][i] = 0.0;
     }
@@ -232,28 +237,30 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceArgs a) {
                     // the last accepted step [t, t + h_abs] crossed an event surface (ivp.py:678-697)
                     const double h = h_abs;
                     double q[4];
-                    dense_coeffs(K[0][IR], K[2][IR], K[3][IR], K[4][IR], K[5][IR], K[6][IR], q);
-                    double x_h = 2.0, x_e = 2.0;
-                    if (state == PEND_H || state == PEND_HE) x_h = event_root(q, y[IR], h, a.r_hor);
-                    if (state == PEND_E || state == PEND_HE) x_e = event_root(q, y[IR], h, a.r_sphere);
-                    const double x = fmin(x_h, x_e);  // earliest terminal event (ivp.py:117-126)
-                    final_status = (x_h <= x_e) ? CAPTURED : ESCAPED;
+                    dense_coeffs_x(k[IR], K[0][IR], K[1][IR], K[2][IR], K[3][IR], K[4][IR], K[5][IR], h, q);
+                    double s_h = 2.0, s_e = 2.0;
+                    if (state == PEND_H || state == PEND_HE) s_h = event_root(q, x[IR], h, a.r_hor);
+                    if (state == PEND_E || state == PEND_HE) s_e = event_root(q, x[IR], h, a.r_sphere);
+                    const double s = fmin(s_h, s_e);  // earliest terminal event (ivp.py:117-126)
+                    final_status = (s_h <= s_e) ? CAPTURED : ESCAPED;
 #pragma unroll
-                    for (int i = 0; i < NS; i++) {
-                        double qi[4];
-                        dense_coeffs(K[0][i], K[2][i], K[3][i], K[4][i], K[5][i], K[6][i], qi);
-                        y[i] = dense_eval(qi, y[i], h, x);
+                    for (int i = 0; i < NK; i++) {
+                        double qk[4], qx[4];
+                        dense_coeffs_x(k[i], K[0][i], K[1][i], K[2][i], K[3][i], K[4][i], K[5][i], h, qx);
+                        dense_coeffs_k(K[0][i], K[2][i], K[3][i], K[4][i], K[5][i], K[6][i], qk);
+                        x[i] = dense_eval(qx, x[i], h, s);
+                        k[i] = dense_eval(qk, k[i], h, s);
                     }
-                    t = fma(x, h, t);
+                    t = fma(s, h, t);
                 }
                 double x0[3] = {0, 0, 0}, k0[3] = {0, 0, 0}, xo[3], ko[3];
-                if (NS == 6) load_ray<AOS>(a, idx, x0, k0);
+                if (NK == 3) load_ray<AOS>(a, idx, x0, k0);
                 if (final_status == START_INSIDE_HOLE) {
 #pragma unroll
                     for (int c = 0; c < 3; c++) xo[c] = ko[c] = __longlong_as_double(0x7ff8000000000000LL);
                 } else {
-                    if (!all_finite<NS>(y)) final_status = STEP_FAILED;
-                    exit_state<NS>(y, x0, k0, xo, ko);
+                    if (!all_finite<NK>(k, x)) final_status = STEP_FAILED;
+                    exit_state<NK>(k, x, x0, k0, xo, ko);
                 }
                 store_ray<AOS>(a, idx, xo, ko, final_status, n_attempt, n_accept);
                 state = LANE_EMPTY;
@@ -276,13 +283,13 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceArgs a) {
                         n_accept = 0;
                         rejected = false;
                         t = 0.0;
-                        if (!init_state<NS>(x0, k0, a.rs, a.r_hor, y)) {
+                        if (!init_state<NK>(x0, k0, a.rs, a.r_hor, k, x)) {
                             state = START_INSIDE_HOLE;
-                        } else if (!all_finite<NS>(y)) {
+                        } else if (!all_finite<NK>(k, x)) {
                             state = STEP_FAILED;  // singular entry (on the polar axis): scipy refuses such a y0
                         } else {
-                            Rhs<NS>::eval(y, a.rs, K[0]);  // f0 (rk.py:94)
-                            h_abs = initial_step<NS>(y, K[0], a.rs, a.rtol, a.atol, t_bound, a.max_step);
+                            Rhs<NK>::eval(k, x, a.rs, K[0]);  // f0 (rk.py:94)
+                            h_abs = initial_step<NK>(k, x, K[0], a.rs, a.rtol, a.atol, t_bound, a.max_step);
                             state = LANE_RUNNING;
                         }
                     }
@@ -299,21 +306,21 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceArgs a) {
                 else if (h_abs < min_step) h_abs = min_step;
             }
             if (h_abs < min_step) {
-                state = STEP_FAILED;  // TOO_SMALL_STEP; y holds the last accepted state
+                state = STEP_FAILED;  // TOO_SMALL_STEP; (k, x) hold the last accepted state
             } else {
                 double t_new = t + h_abs;
                 if (t_new - t_bound > 0.0) t_new = t_bound;
                 const double h = t_new - t;
                 h_abs = fabs(h);
                 n_attempt++;
-                const double esum = rk45_attempt<NS>(y, K, yn, h, a.rs, a.rtol, a.atol);
-                const double en2 = esum * (1.0 / NS);  // (RMS error norm)^2
+                const double esum = rk45_attempt<NK>(k, x, K, kn, xn, h, a.rs, a.rtol, a.atol);
+                const double en2 = esum * (1.0 / (2 * NK));  // (RMS error norm)^2 over all 2 NK components
                 if (en2 < 1.0) {
                     n_accept++;
                     const double factor = step_factor(en2, 0.2, rejected ? 1.0 : 10.0);
                     // events on the accepted step (ivp.py:134-158): horizon either direction, sphere upward
-                    const double gh0 = y[IR] - a.r_hor, gh1 = yn[IR] - a.r_hor;
-                    const double ge0 = y[IR] - a.r_sphere, ge1 = yn[IR] - a.r_sphere;
+                    const double gh0 = x[IR] - a.r_hor, gh1 = xn[IR] - a.r_hor;
+                    const double ge0 = x[IR] - a.r_sphere, ge1 = xn[IR] - a.r_sphere;
                     const bool act_h = (gh0 <= 0.0 && gh1 >= 0.0) || (gh0 >= 0.0 && gh1 <= 0.0);
                     const bool act_e = a.has_outer && (ge0 <= 0.0 && ge1 >= 0.0);
                     if (act_h || act_e) {
@@ -324,8 +331,9 @@ __global__ void __launch_bounds__(128) trace_kernel(const TraceArgs a) {
                         t = t_new;
                         rejected = false;
 #pragma unroll
-                        for (int i = 0; i < NS; i++) {
-                            y[i] = yn[i];
+                        for (int i = 0; i < NK; i++) {
+                            k[i] = kn[i];
+                            x[i] = xn[i];
                             K[0][i] = K[6][i];  // FSAL
                         }
                         if (t - t_bound >= 0.0) state = LAMBDA_EXHAUSTED;

@@ -110,8 +110,9 @@ int bhg_sum_counters(const int32_t* counters_dev, const int32_t* status_dev, int
 int64_t bhg_launch_count(void);
 
 /* Device-side numerical self-test of the FP64 building blocks (reciprocal, inverse tenth root, RHS against
- * IEEE division form).  Writes max relative errors to out[0..3]; returns 0 if all are within bounds. */
-int bhg_selftest(int32_t device, double* out4);
+ * IEEE division form, table sincos against the library).  Writes 8 doubles of max errors to out8 (NULL ok);
+ * returns 0 if all are within bounds. */
+int bhg_selftest(int32_t device, double* out8);
 
 /* FP64 FMA throughput microbenchmark (dependent-free DFMA chains, all SMs), in TFLOP/s; used as the
  * measured roofline denominator because MEASURED_PEAKS.json carries no FP64 entry. */
