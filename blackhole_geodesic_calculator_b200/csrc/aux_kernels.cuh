@@ -38,18 +38,18 @@ __device__ __forceinline__ void atomic_max_double(double* addr, double v) {
 
 // out[0]: max rel. error of fast_rcp vs IEEE 1/a ; out[1]: inv_tenth_root vs pow(a,-0.1) ;
 // out[2]: RHS (reciprocal form) vs the textbook division form ; out[3]: 3-DFMA reciprocal ;
-// out[4]: table sincos vs library sincos (absolute)
+// out[4]: table sincos vs library sincos (absolute) ; out[5]: fifth_root vs pow(a, 0.2)
 __global__ void selftest_kernel(double* out) {
     const int gid = blockIdx.x * blockDim.x + threadIdx.x;
     const int nth = gridDim.x * blockDim.x;
-    double e_rcp = 0, e_root = 0, e_rhs = 0, e_rcp3 = 0, e_sc = 0;
+    double e_rcp = 0, e_root = 0, e_rhs = 0, e_rcp3 = 0, e_sc = 0, e_root5 = 0;
     for (int j = gid; j < nth * 16; j += nth) {
         // log-uniform-ish positive and negative operands
         const double u = (j + 0.5) / (nth * 16.0);
         const double a = exp((u - 0.5) * 80.0) * ((j & 1) ? -1.0 : 1.0);
-        const double r0 = 1.0 / a, r1 = fast_rcp(a);
+        const double r0 = 1.0 / a, r1 = fast_rcp5(a);
         e_rcp = fmax(e_rcp, fabs(r1 - r0) / fabs(r0));
-        e_rcp3 = fmax(e_rcp3, fabs(fast_rcp3(a) - r0) / fabs(r0));
+        e_rcp3 = fmax(e_rcp3, fabs(fast_rcp(a) - r0) / fabs(r0));
         {
             // table sincos vs the library over |x| < 40
             const double xs = (u - 0.5) * 80.0;
@@ -62,6 +62,8 @@ __global__ void selftest_kernel(double* out) {
         if (b > 1e-12 && b < 1e8) {
             const double p0 = pow(b, -0.1), p1 = inv_tenth_root(b);
             e_root = fmax(e_root, fabs(p1 - p0) / p0);
+            const double w0 = pow(b, 0.2), w1 = fifth_root(b);
+            e_root5 = fmax(e_root5, fabs(w1 - w0) / w0);
         }
         // RHS comparison at a generic state
         const double r = 2.2 + 60.0 * u, th = 0.05 + 3.0 * u, rs = 2.0;
@@ -83,6 +85,7 @@ __global__ void selftest_kernel(double* out) {
     atomic_max_double(&out[2], e_rhs);
     atomic_max_double(&out[3], e_rcp3);
     atomic_max_double(&out[4], e_sc);
+    atomic_max_double(&out[5], e_root5);
 }
 
 // 16 independent DFMA chains per thread; flops = 2 * 16 * iters per thread

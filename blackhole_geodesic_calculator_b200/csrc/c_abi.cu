@@ -291,7 +291,7 @@ int bhg_selftest(int32_t device, double* out8) {
     cudaFree(d);
     if (out8) memcpy(out8, h, sizeof(h));
     // reciprocal and tenth root to a few ulp; RHS forms agree to rounding; sincos exact by construction
-    if (!(h[0] < 1e-15) || !(h[1] < 4e-15) || !(h[2] < 1e-12) || !(h[4] < 4e-16)) return fail(BHG_ERR_CUDA, "selftest out of bounds: rcp %.3e root %.3e rhs %.3e", h[0], h[1], h[2]);
+    if (!(h[0] < 1e-15) || !(h[1] < 4e-15) || !(h[2] < 1e-12) || !(h[3] < 1e-15) || !(h[4] < 4e-16) || !(h[5] < 4e-15)) return fail(BHG_ERR_CUDA, "selftest out of bounds: rcp %.3e root %.3e rhs %.3e", h[0], h[1], h[2]);
     return 0;
 }
 

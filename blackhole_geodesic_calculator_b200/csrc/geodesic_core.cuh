@@ -50,8 +50,8 @@ enum LaneState : int {
 
 // 1/a for normal, finite a (call sites guarantee that, or produce NaN/inf that the step controller
 // rejects): MUFU.RCP64H seed, one third-order and one second-order refinement (5 DFMA).  Measured on
-// B200 against IEEE division: identical results on the self-test sweep (profiles/r1a).
-__device__ __forceinline__ double fast_rcp(double a) {
+// B200 against IEEE division: bit-identical on the self-test sweep (profiles/r1b_selftest.txt).
+__device__ __forceinline__ double fast_rcp5(double a) {
     double x0;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(a));
     double e = fma(-a, x0, 1.0);
@@ -61,8 +61,9 @@ __device__ __forceinline__ double fast_rcp(double a) {
     return fma(x1, e3, x1);
 }
 
-// 3-DFMA variant (seed + one third-order step), used where a few ulp are irrelevant
-__device__ __forceinline__ double fast_rcp3(double a) {
+// 3-DFMA variant (seed + one third-order step): measured max relative error 2.2e-16 (1 ulp) on B200.
+// This is the reciprocal of the hot loop.
+__device__ __forceinline__ double fast_rcp(double a) {
     double x0;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(a));
     double e = fma(-a, x0, 1.0);
@@ -84,6 +85,21 @@ __device__ __forceinline__ double inv_tenth_root(double a) {
         x = x * r * 0.1;
     }
     return x;
+}
+
+// a^(1/5) for a in [1e-30, 1e30] (initial-step heuristic): Newton on x^-5 = a for the inverse root, then
+// a * x^4.  Float seed 1e-5 -> two steps -> 1e-18.
+__device__ __forceinline__ double fifth_root(double a) {
+    float af = (float)a;
+    double x = (double)exp2f(-0.2f * log2f(af));
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        double x2 = x * x;
+        double x5 = x2 * x2 * x;
+        x = x * fma(-a, x5, 6.0) * 0.2;
+    }
+    double x2 = x * x;
+    return a * (x2 * x2);
 }
 
 // sin and cos, < 1 ulp each: Cody-Waite reduction by pi/2 in two parts (exact for |n| < 2^20) and the
@@ -283,29 +299,45 @@ __device__ __forceinline__ double rk45_attempt(const double (&k)[NK], const doub
     }
     Rhs<NK>::eval(kn, xn, rs, K[6]);
     // ---- error estimate, scaled (rk.py:143-146, common.py:63-65)
-    double esum = 0.0;
+    double ek[NK], ex[NK], sk[NK], sx[NK];
 #pragma unroll
     for (int i = 0; i < NK; i++) {
-        double ek = TAB(E1) * K[0][i];
-        ek = fma(TAB(E3), K[2][i], ek);
-        ek = fma(TAB(E4), K[3][i], ek);
-        ek = fma(TAB(E5), K[4][i], ek);
-        ek = fma(TAB(E6), K[5][i], ek);
-        ek = fma(TAB(E7), K[6][i], ek);
-        double ex = TAB(EA1) * K[0][i];
-        ex = fma(TAB(EA2), K[1][i], ex);
-        ex = fma(TAB(EA3), K[2][i], ex);
-        ex = fma(TAB(EA4), K[3][i], ex);
-        ex = fma(TAB(EA5), K[4][i], ex);
-        ex = fma(TAB(EA6), K[5][i], ex);
-        const double sk = fma(fmax(fabs(k[i]), fabs(kn[i])), rtol, atol);
-        const double sx = fma(fmax(fabs(x[i]), fabs(xn[i])), rtol, atol);
-        // one reciprocal for the pair
-        const double inv = fast_rcp(sk * sx);
-        const double qk = (ek * h) * (inv * sx);
-        const double qx = (ex * h2) * (inv * sk);
-        esum = fma(qk, qk, esum);
-        esum = fma(qx, qx, esum);
+        double e = TAB(E1) * K[0][i];
+        e = fma(TAB(E3), K[2][i], e);
+        e = fma(TAB(E4), K[3][i], e);
+        e = fma(TAB(E5), K[4][i], e);
+        e = fma(TAB(E6), K[5][i], e);
+        ek[i] = fma(TAB(E7), K[6][i], e) * h;
+        double g = TAB(EA1) * K[0][i];
+        g = fma(TAB(EA2), K[1][i], g);
+        g = fma(TAB(EA3), K[2][i], g);
+        g = fma(TAB(EA4), K[3][i], g);
+        g = fma(TAB(EA5), K[4][i], g);
+        ex[i] = fma(TAB(EA6), K[5][i], g) * h2;
+        sk[i] = fma(fmax(fabs(k[i]), fabs(kn[i])), rtol, atol);
+        sx[i] = fma(fmax(fabs(x[i]), fabs(xn[i])), rtol, atol);
+    }
+    // one reciprocal per group of four scales (two momentum/position pairs); scales are >= atol so the
+    // products neither overflow nor underflow
+    double esum = 0.0;
+#pragma unroll
+    for (int i = 0; i + 1 < NK; i += 2) {
+        const double pa = sk[i] * sx[i], pb = sk[i + 1] * sx[i + 1];
+        const double inv = fast_rcp(pa * pb);
+        const double ia = inv * pb, ib = inv * pa;  // 1/pa, 1/pb
+        const double q0 = ek[i] * (ia * sx[i]), q1 = ex[i] * (ia * sk[i]);
+        const double q2 = ek[i + 1] * (ib * sx[i + 1]), q3 = ex[i + 1] * (ib * sk[i + 1]);
+        esum = fma(q0, q0, esum);
+        esum = fma(q1, q1, esum);
+        esum = fma(q2, q2, esum);
+        esum = fma(q3, q3, esum);
+    }
+    if (NK & 1) {
+        constexpr int i = NK - 1;
+        const double inv = fast_rcp(sk[i] * sx[i]);
+        const double q0 = ek[i] * (inv * sx[i]), q1 = ex[i] * (inv * sk[i]);
+        esum = fma(q0, q0, esum);
+        esum = fma(q1, q1, esum);
     }
     return esum;
 }
@@ -337,8 +369,8 @@ __device__ __forceinline__ double initial_step(const double (&k)[NK], const doub
     double d0 = 0.0, d1 = 0.0;
 #pragma unroll
     for (int i = 0; i < NK; i++) {
-        isk[i] = 1.0 / fma(fabs(k[i]), rtol, atol);
-        isx[i] = 1.0 / fma(fabs(x[i]), rtol, atol);
+        isk[i] = fast_rcp5(fma(fabs(k[i]), rtol, atol));
+        isx[i] = fast_rcp5(fma(fabs(x[i]), rtol, atol));
         const double a = k[i] * isk[i], b = x[i] * isx[i];
         const double c = K0[i] * isk[i], d = k[i] * isx[i];
         d0 = fma(a, a, fma(b, b, d0));
@@ -365,7 +397,10 @@ __device__ __forceinline__ double initial_step(const double (&k)[NK], const doub
     d2 = sqrt(d2 / (2 * NK)) / h0;
     double h1;
     if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
-    else h1 = pow(0.01 / fmax(d1, d2), 0.2);
+    else {
+        const double arg = 0.01 / fmax(d1, d2);
+        h1 = (arg > 1e-30 && arg < 1e30) ? fifth_root(arg) : pow(arg, 0.2);
+    }
     return fmin(fmin(100.0 * h0, h1), fmin(interval, max_step));
 }
 
@@ -418,7 +453,7 @@ __device__ __forceinline__ double event_root(const double (&q)[4], double rold, 
         if (fs == 0.0) return s;
         if ((fs < 0.0) == lo_neg) lo = s; else hi = s;
         const double dfs = h * fma(4.0 * q[3], s * s * s, fma(3.0 * q[2], s * s, fma(2.0 * q[1], s, q[0])));
-        double sn = s - fs / dfs;
+        double sn = fma(-fs, fast_rcp(dfs), s);
         if (!(sn > lo && sn < hi)) sn = 0.5 * (lo + hi);
         if (fabs(sn - s) <= 2.220446049250313e-16 * fmax(fabs(sn), 1e-3) || hi - lo <= 4.4e-16 * hi) return sn;
         s = sn;

@@ -146,8 +146,8 @@ template <>
 __device__ __forceinline__ void exit_state<4>(const double (&k)[4], const double (&x)[4], const double (&)[3],
                                               const double (&)[3], double (&xo)[3], double (&ko)[3]) {
     double st, ct, sp, cp;
-    sincos(x[2], &st, &ct);
-    sincos(x[3], &sp, &cp);
+    sincos_tab(x[2], &st, &ct);
+    sincos_tab(x[3], &sp, &cp);
     const double R = x[1], k_r = k[1], k_th = k[2], k_ph = k[3];
     xo[0] = R * st * cp;
     xo[1] = R * st * sp;
@@ -169,7 +169,7 @@ __device__ __forceinline__ void exit_state<3>(const double (&k)[3], const double
     double r0, kr0, wn, e1[3], e2[3];
     plane_frame(x0, k0, r0, kr0, wn, e1, e2);
     double sp, cp;
-    sincos(x[2], &sp, &cp);
+    sincos_tab(x[2], &sp, &cp);
     const double R = x[1];
     const double a = fma(k[1], cp, -R * sp * k[2]);
     const double b = fma(k[1], sp, R * cp * k[2]);
