@@ -187,7 +187,7 @@ def run_b200(args):
     exit_pos, exit_dir = torch.empty_like(pos), torch.empty_like(pos)
     status = torch.empty(n, dtype=torch.int32, device=dev)
     counters = torch.empty((2, n), dtype=torch.int32, device=dev)
-    params = api.make_params(mode=args.mode, refill_threshold=args.threshold)
+    params = api.make_params(mode=args.mode, refill_threshold=args.threshold, image_width=0 if args.no_tiles else W)
     stream = torch.cuda.current_stream(dev)
 
     def step(with_counters=False):
@@ -273,6 +273,7 @@ def run_b200(args):
                                    "seed 42; at N>1 rank r integrates animation frame r (config 4, camera azimuth "
                                    "+3.6 deg/frame)",
                        "mode": args.mode, "refill_threshold": args.threshold or 32,
+                       "image_width_hint": 0 if args.no_tiles else W,
                        "rays_per_step_per_gpu": n, "cache": "inputs+outputs 525 MB per step > 126 MB L2 (no flush)",
                        "mean_attempts_per_ray": att / n},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n * 48, "d2h_bytes_per_step": n * 52,
@@ -321,6 +322,7 @@ def main():
     ap.add_argument("--mode", default="parity", choices=["parity", "plane"])
     ap.add_argument("--threshold", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tiles", action="store_true", help="do not pass the image_width scheduling hint")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

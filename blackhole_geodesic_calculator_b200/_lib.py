@@ -25,6 +25,8 @@ class BhgParams(ctypes.Structure):
         ("lambda_max", ctypes.c_double),
         ("mode", ctypes.c_int32),
         ("refill_threshold", ctypes.c_int32),
+        ("image_width", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
     ]
 
 

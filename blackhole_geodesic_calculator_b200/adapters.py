@@ -1,0 +1,175 @@
+"""Host-side mirrors of the reference's call shapes for the geodesic path, on top of the batched `trace()`.
+
+The reference engines reach the solver through three curvedpy interfaces (curvedpy itself is not part of the
+reference repository); each class below keeps the names, argument meaning and result layout visible at the
+reference's call sites, and adds a `*_batch` method that does a whole frame or tile in one GPU call:
+
+  * `GeodesicIntegratorSchwarzschild.calc_trajectory`  <- raytracer/RelativisticRenderEngine.py:134,293-297,307-310
+  * `SchwarzschildGeodesic.ray_trace` / `.approximateCurveEnd`
+                                                       <- raytracer/LimitedRelativisticRenderEngine.py:90,273-279,308-319
+  * `RelativisticCamera.run` / `.ray_blackhole_hit` / `.ray_end`
+                                                       <- raytracer/RelativisticRenderEngineCamEdition.py:206-215,225-228
+
+Out of scope here (SURVEY.md section 8f "next" row 2): the dense trajectory polylines that `checkHitDisk`
+(LimitedRelativisticRenderEngine.py:413-438) scans; the polyline outputs below hold the entry and end states
+only.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import api, raygen
+
+
+class GeodesicIntegratorSchwarzschild:
+    """RRE call shape: fixed affine length, no sphere; end state = last sample (RRE.py:293-294,307-308)."""
+
+    def __init__(self, mass=1.0, time_like=False, verbose=False, device=0, rtol=1e-3, atol=1e-6, eps_horizon=0.01):
+        if time_like:
+            raise NotImplementedError("only null geodesics (time_like=False) are on the reference's render path "
+                                      "(RelativisticRenderEngine.py:134)")
+        self.mass = float(mass)
+        self.r_s = 2.0 * self.mass
+        self.device = device
+        self.rtol, self.atol, self.eps_horizon = rtol, atol, eps_horizon
+
+    def calc_trajectories_batch(self, k0_xyz, x0_xyz, max_step=math.inf, curve_end=50.0, R_end=math.inf, mode="parity"):
+        """k0_xyz, x0_xyz: [N,3].  Returns (end_dir[N,3] unit, end_loc[N,3], hit_blackhole[N] bool,
+        start_inside_hole[N] bool, status[N])."""
+        x0 = np.ascontiguousarray(x0_xyz, dtype=np.float64).reshape(-1, 3)
+        k0 = np.ascontiguousarray(k0_xyz, dtype=np.float64).reshape(-1, 3)
+        r_sphere = float(R_end)
+        exit_pos, exit_dir, status = api.trace(x0, k0, self.mass, r_sphere, self.rtol, self.atol, max_step=max_step,
+                                               eps_horizon=self.eps_horizon, lambda_max=float(curve_end), mode=mode,
+                                               device=self.device)
+        return exit_dir, exit_pos, status == api.CAPTURED, status == api.START_INSIDE_HOLE, status
+
+    def calc_trajectory(self, k0_xyz, x0_xyz, max_step=math.inf, curve_end=50.0, nr_points_curve=50, verbose=False):
+        """Per-ray drop-in: returns (k_xyz[3,2], x_xyz[3,2], result) — columns are the start and the end state
+        (the reference engine reads column -1 only, RelativisticRenderEngine.py:307-308)."""
+        k0 = np.asarray(k0_xyz, dtype=np.float64).reshape(1, 3)
+        x0 = np.asarray(x0_xyz, dtype=np.float64).reshape(1, 3)
+        end_dir, end_loc, hit, inside, status = self.calc_trajectories_batch(k0, x0, max_step, curve_end)
+        result = {"start_inside_hole": bool(inside[0]), "hit_blackhole": bool(hit[0]), "status": int(status[0])}
+        k_xyz = np.stack([k0[0], end_dir[0]], axis=1)
+        x_xyz = np.stack([x0[0], end_loc[0]], axis=1)
+        return k_xyz, x_xyz, result
+
+
+def spacetime_ray_cast_batch(integrator: GeodesicIntegratorSchwarzschild, origin, directions, bh_loc=(0.0, 0.0, 0.0),
+                             max_step=math.inf, curve_end=50.0):
+    """Batched body of `RelativisticRenderEngine.spacetime_ray_cast` (RRE.py:271-313) for one camera origin
+    and N primary directions: returns (hit[N], hit_bh[N], end_dir[N,3], end_loc[N,3]) with `hit` all False
+    exactly as the reference hard-wires it (RRE.py:305)."""
+    d = np.ascontiguousarray(directions, dtype=np.float64).reshape(-1, 3)
+    o = np.asarray(origin, dtype=np.float64) - np.asarray(bh_loc, dtype=np.float64)
+    x0 = np.broadcast_to(o, d.shape).copy()
+    end_dir, end_loc, hit_bh, inside, _ = integrator.calc_trajectories_batch(d, x0, max_step, curve_end)
+    hit_bh = hit_bh | inside  # "Camera INSIDE blackhole" returns hit_bh=True (RRE.py:311-313)
+    return np.zeros(d.shape[0], bool), hit_bh, end_dir, end_loc
+
+
+class SchwarzschildGeodesic:
+    """LIM call shape: entry point on the sphere of influence -> exit point/direction or capture
+    (LimitedRelativisticRenderEngine.py:273-278).  The solver works in units of r_s (M = 1/2): the sphere
+    object of radius |loc_hit| is `ratio_obj_to_blackhole` horizon radii large (LIM.py:488, README.md:60)."""
+
+    def __init__(self, metric="schwarzschild", device=0, rtol=1e-3, atol=1e-6, eps_horizon=0.01):
+        if metric != "schwarzschild":
+            raise NotImplementedError(f"metric {metric!r}: only 'schwarzschild' is on the reference's render path")
+        self.metric = metric
+        self.device = device
+        self.rtol, self.atol, self.eps_horizon = rtol, atol, eps_horizon
+
+    @staticmethod
+    def approximateCurveEnd(ratio_obj_to_blackhole):
+        """Affine-length bound in r_s units.  curvedpy's own formula is not in the reference; its commented
+        predecessor is `50 + 2*50*(ratio/20 - 1)` (LIM.py:279), which under-runs for small spheres, so the
+        bound used is the larger of that and 10 sphere radii (a bound that is not reached changes nothing)."""
+        r = float(ratio_obj_to_blackhole)
+        return max(50.0 + 2.0 * 50.0 * (r / 20.0 - 1.0), 10.0 * r)
+
+    def ray_trace_batch(self, directions, loc_hits, exit_tolerance=0.2, ratio_obj_to_blackhole=30.0, curve_end=None,
+                        max_step=math.inf, mode="parity"):
+        """directions, loc_hits: [N,3] in scene units, relative to the sphere centre.  Returns
+        (end_loc[N,3] scene units, end_dir[N,3] unit, hit_blackhole[N], outside[N], status[N])."""
+        d = np.ascontiguousarray(directions, dtype=np.float64).reshape(-1, 3)
+        p = np.ascontiguousarray(loc_hits, dtype=np.float64).reshape(-1, 3)
+        ratio = float(ratio_obj_to_blackhole)
+        scale = ratio / np.linalg.norm(p, axis=1)          # scene units -> r_s units, per ray
+        lam = self.approximateCurveEnd(ratio) if curve_end is None else float(curve_end)
+        ms = math.inf if (max_step is None or max_step == -1) else float(max_step)
+        exit_pos, exit_dir, status = api.trace(p * scale[:, None], d, 0.5, ratio, self.rtol, self.atol, max_step=ms,
+                                               eps_horizon=self.eps_horizon, lambda_max=lam, mode=mode,
+                                               device=self.device)
+        hit_bh = status == api.CAPTURED
+        # 'Outside': the ray did not end on the sphere within exit_tolerance (LIM.py:311-314)
+        off = np.abs(np.linalg.norm(exit_pos, axis=1) - ratio) > exit_tolerance
+        outside = ~hit_bh & (off | (status != api.ESCAPED))
+        return exit_pos / scale[:, None], exit_dir, hit_bh, outside, status
+
+    def ray_trace(self, direction, loc_hit, exit_tolerance=0.2, ratio_obj_to_blackhole=30.0, curve_end=None,
+                  max_step=math.inf, warnings=False):
+        """Per-ray drop-in: (x, y, z, end_loc, end_dir, mes); x, y, z hold the entry and end points."""
+        end_loc, end_dir, hit_bh, outside, status = self.ray_trace_batch(
+            np.asarray(direction, float).reshape(1, 3), np.asarray(loc_hit, float).reshape(1, 3), exit_tolerance,
+            ratio_obj_to_blackhole, curve_end, max_step)
+        mes = {"hit_blackhole": bool(hit_bh[0]), "status": int(status[0])}
+        if outside[0]:
+            mes["error"] = "Outside"
+        loc = np.asarray(loc_hit, float).reshape(3)
+        xyz = np.stack([loc, end_loc[0]], axis=1)
+        return xyz[0], xyz[1], xyz[2], end_loc[0], end_dir[0], mes
+
+
+class RelativisticCamera:
+    """CAM call shape: a whole frame traced ahead of shading; the consumer reads `ray_blackhole_hit[iy,ix]`
+    and `ray_end[iy,ix,3:6]` (RelativisticRenderEngineCamEdition.py:206-215,225-228).  `a` (spin) must be 0:
+    only Schwarzschild is on the path."""
+
+    def __init__(self, resolution=(64, 64), field_of_view=(0.6, 0.6), a=0.0, M=1.0, camera_location=raygen.CFG_CAMERA_POS,
+                 camera_rotation_euler=None, r_sphere=raygen.CFG_R_SPHERE, samples=1, seed=raygen.CFG_SEED,
+                 jitter="none", max_step=math.inf, verbose=False, device=0):
+        if a != 0.0:
+            raise NotImplementedError("Kerr (a != 0) is not on the reference's render path")
+        self.resolution = (int(resolution[0]), int(resolution[1]))  # [height, width] (CamEdition.py:206)
+        self.field_of_view = (float(field_of_view[0]), float(field_of_view[1]))
+        self.M, self.r_sphere = float(M), float(r_sphere)
+        self.camera_location = np.asarray(camera_location, dtype=np.float64)
+        self.rotation = (raygen.look_at_rotation(self.camera_location) if camera_rotation_euler is None
+                         else raygen.euler_xyz_rotation(*camera_rotation_euler))
+        self.samples, self.seed, self.jitter, self.max_step, self.device = samples, seed, jitter, max_step, device
+        self.ray_blackhole_hit = None
+        self.ray_end = None
+        self.ray_status = None
+
+    def run(self, verbose=False, verbose_lvl=0, mode="parity"):
+        h, w = self.resolution
+        d = raygen.camera_rays(w, h, self.samples, self.field_of_view[0], self.field_of_view[1], self.rotation,
+                               self.seed, self.jitter)
+        p, hit = raygen.sphere_entry(self.camera_location, d, self.r_sphere)
+        n = d.shape[0]
+        exit_pos = np.full((n, 3), np.nan)
+        exit_dir = d.copy()                      # rays that miss the sphere keep their flat direction
+        status = np.full(n, -1, dtype=np.int32)  # -1: never entered the curved region
+        if hit.any():
+            ep, ed, st = api.trace(p[hit], d[hit], self.M, self.r_sphere, max_step=self.max_step, mode=mode,
+                                   device=self.device)
+            exit_pos[hit], exit_dir[hit], status[hit] = ep, ed, st
+        shape = (self.samples, h, w) if self.samples > 1 else (h, w)
+        self.ray_status = status.reshape(shape)
+        self.ray_blackhole_hit = (status == api.CAPTURED).astype(np.int64).reshape(shape)
+        self.ray_end = np.concatenate([exit_pos, exit_dir], axis=1).reshape(shape + (6,))
+        return self
+
+    def save(self, path):
+        np.savez_compressed(path, ray_blackhole_hit=self.ray_blackhole_hit, ray_end=self.ray_end,
+                            ray_status=self.ray_status, resolution=self.resolution, field_of_view=self.field_of_view,
+                            M=self.M, r_sphere=self.r_sphere, camera_location=self.camera_location)
+
+    def load(self, path):
+        z = np.load(path)
+        self.ray_blackhole_hit, self.ray_end, self.ray_status = z["ray_blackhole_hit"], z["ray_end"], z["ray_status"]
+        return self

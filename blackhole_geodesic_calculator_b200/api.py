@@ -28,13 +28,14 @@ LAYOUT_SOA, LAYOUT_AOS = 0, 1
 
 
 def make_params(M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, max_step=math.inf, eps_horizon=0.01,
-                lambda_max=None, mode="parity", refill_threshold=0) -> BhgParams:
+                lambda_max=None, mode="parity", refill_threshold=0, image_width=0) -> BhgParams:
     if mode not in MODES:
         raise ValueError(f"mode must be one of {sorted(MODES)}, got {mode!r}")
     if max_step is None or max_step == -1:  # the reference maps -1 to inf (RelativisticRenderEngine.py:59-60)
         max_step = math.inf
     return BhgParams(float(M), float(r_sphere), float(rtol), float(atol), float(max_step), float(eps_horizon),
-                     0.0 if lambda_max is None else float(lambda_max), MODES[mode], int(refill_threshold))
+                     0.0 if lambda_max is None else float(lambda_max), MODES[mode], int(refill_threshold),
+                     int(image_width), 0)
 
 
 def _is_torch(x):
@@ -42,16 +43,19 @@ def _is_torch(x):
 
 
 def trace(entry_pos, entry_dir, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, *, max_step=math.inf,
-          eps_horizon=0.01, lambda_max=None, mode="parity", refill_threshold=0, device=0,
+          eps_horizon=0.01, lambda_max=None, mode="parity", refill_threshold=0, image_width=0, device=0,
           return_counters=False):
     """Integrate N Schwarzschild null geodesics from sphere entry to exit or capture.
 
     entry_pos, entry_dir : [N,3] float64, BH-centred position and coordinate direction (numpy arrays on the
         host, or torch CUDA tensors, which are processed in place on their device and stream).
+    image_width : optional scheduling hint — the rays are a row-major image of this width (the reference's
+        s -> y -> x order); warps then integrate 8 x 4 pixel tiles.  Never changes results.
     Returns (exit_pos[N,3], exit_dir[N,3] unit-norm, status[N] int32) and, with return_counters, an
     int32 [2,N] array of (RK45 attempts, accepted steps).
     """
-    params = make_params(M, r_sphere, rtol, atol, max_step, eps_horizon, lambda_max, mode, refill_threshold)
+    params = make_params(M, r_sphere, rtol, atol, max_step, eps_horizon, lambda_max, mode, refill_threshold,
+                         image_width)
     if _is_torch(entry_pos):
         return _trace_torch(entry_pos, entry_dir, params, return_counters)
     lib = _lib.load()

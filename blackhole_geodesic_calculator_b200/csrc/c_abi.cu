@@ -110,6 +110,8 @@ int validate(const bhg_params* p, long long n) {
         return fail(BHG_ERR_INVALID_ARGUMENT, "unknown mode %d", p->mode);
     if (p->refill_threshold < 0 || p->refill_threshold > 32)
         return fail(BHG_ERR_INVALID_ARGUMENT, "refill_threshold must be in 0..32");
+    if (p->image_width < 0 || p->reserved != 0)
+        return fail(BHG_ERR_INVALID_ARGUMENT, "image_width must be >= 0 and reserved must be 0");
     double lam = p->lambda_max;
     if (!(lam > 0.0) && !std::isfinite(p->r_sphere))
         return fail(BHG_ERR_INVALID_ARGUMENT, "lambda_max must be given when r_sphere is infinite");
@@ -131,6 +133,8 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
     a.rtol = p->rtol; a.atol = p->atol; a.max_step = p->max_step;
     a.lambda_max = p->lambda_max > 0.0 ? p->lambda_max : 10.0 * p->r_sphere;
     a.refill_threshold = p->refill_threshold > 0 ? p->refill_threshold : 32;
+    a.tile_width = (p->image_width > 0 && p->image_width % 8 == 0 && n % (4LL * p->image_width) == 0 && !order)
+                       ? p->image_width : 0;
     unsigned slot = c.next_slot.fetch_add(1) % kQueueSlots;
     a.queue_head = c.queue_slots + slot;
     BHG_CUDA(cudaMemsetAsync(a.queue_head, 0, sizeof(unsigned long long), stream));
@@ -165,6 +169,8 @@ void bhg_default_params(bhg_params* p) {
     p->lambda_max = 0.0;
     p->mode = BHG_MODE_PARITY;
     p->refill_threshold = 0;
+    p->image_width = 0;
+    p->reserved = 0;
 }
 
 int bhg_trace_schwarzschild_f64(const double* in, const double* in_dir, double* out, double* out_dir,
@@ -212,7 +218,11 @@ int bhg_trace_schwarzschild_f64_host(const double* entry_pos, const double* entr
     int32_t* d_status = (int32_t*)(base + 4 * vec);
     int32_t* d_cnt = d_status + n;  // 2 n
     // chunked pipeline over 3 streams: H2D(i+1) overlaps trace(i) overlaps D2H(i-1)
-    const long long chunk = n <= (1 << 16) ? n : (n <= (1 << 20) ? (n + 3) / 4 : (1 << 18));
+    long long chunk = n <= (1 << 16) ? n : (n <= (1 << 20) ? (n + 3) / 4 : (1 << 18));
+    if (params->image_width > 0 && n > chunk) {  // keep whole 4-row bands in a chunk so the tile hint survives
+        const long long band = 4LL * params->image_width;
+        chunk = ((chunk + band - 1) / band) * band;
+    }
     int si = 0;
     for (long long b = 0; b < n; b += chunk, si = (si + 1) % 3) {
         const long long m = (n - b < chunk) ? (n - b) : chunk;

@@ -31,7 +31,22 @@ struct TraceArgs {
     double rs, r_hor, r_sphere, rtol, atol, max_step, lambda_max;
     int has_outer;
     int refill_threshold;
+    int tile_width;  // > 0: queue slots enumerate 8 x 4 pixel tiles of a row-major image of this width
 };
+
+// queue slot -> ray index.  With the image hint, 32 consecutive slots (one warp's fetch when it starts empty)
+// cover an 8 x 4 pixel tile, whose rays have far more similar step counts than 32 pixels of one row.
+__device__ __forceinline__ long long slot_to_ray(const TraceArgs& a, long long slot) {
+    if (a.order) return (long long)__ldg(a.order + slot);
+    if (a.tile_width > 0) {
+        const long long band_sz = 4LL * a.tile_width;           // 4 image rows
+        const long long band = slot / band_sz;
+        const int t = (int)(slot - band * band_sz);
+        const int tile = t >> 5, l = t & 31;
+        return band * band_sz + (long long)(l >> 3) * a.tile_width + (tile << 3) + (l & 7);
+    }
+    return slot;
+}
 
 // pending-event encodings (all < LANE_RUNNING)
 constexpr int PEND_H = -2;   // horizon event active in the last step
@@ -276,7 +291,7 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
                 if (state == LANE_EMPTY) {
                     const long long slot = (long long)base + __popc(idle & lt_mask);
                     if (slot < a.n) {
-                        idx = a.order ? (long long)__ldg(a.order + slot) : slot;
+                        idx = slot_to_ray(a, slot);
                         double x0[3], k0[3];
                         load_ray<AOS>(a, idx, x0, k0);
                         n_attempt = 0;

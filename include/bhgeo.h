@@ -68,6 +68,12 @@ typedef struct bhg_params {
     double lambda_max;  /* affine-length bound (curve_end, RRE.py:61,294); <= 0 selects 10 r_sphere */
     int32_t mode;       /* enum bhg_mode                                                   */
     int32_t refill_threshold; /* warp work queue: idle lanes that trigger a refill, 1..32; 0 = default */
+    int32_t image_width;      /* coherence hint: the rays are a row-major image (or stack of images) of this
+                                 width, as the reference's s -> y -> x loop produces them (RRE.py:195-218); the
+                                 queue then hands every warp an 8 x 4 pixel tile instead of 32 pixels of one row.
+                                 0 = no hint.  Ignored unless image_width % 8 == 0 and n % (4 image_width) == 0.
+                                 Scheduling only: results are bit-identical with and without the hint.       */
+    int32_t reserved;         /* must be 0 */
 } bhg_params;
 
 /* Fills *p with the reference defaults (M=1, r_sphere=60, rtol=1e-3, atol=1e-6, max_step=inf,

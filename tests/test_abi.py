@@ -39,7 +39,7 @@ def test_version_and_defaults():
 
 
 def test_params_struct_layout():
-    assert ctypes.sizeof(_lib.BhgParams) == 7 * 8 + 2 * 4
+    assert ctypes.sizeof(_lib.BhgParams) == 7 * 8 + 4 * 4
 
 
 @pytest.mark.parametrize("kw,frag", [

@@ -89,6 +89,10 @@ def test_device_entry_layouts_order_and_thresholds_are_bitwise_identical(api):
         out = [t.cpu().numpy() for t in api.trace(pos, d, refill_threshold=T)]
         for a, b in zip(base, out):
             assert np.array_equal(a, b, equal_nan=True), f"threshold {T}"
+    for wdt in (64, 8, 24, 100):  # 100: not a multiple of 8 -> hint ignored
+        out = [t.cpu().numpy() for t in api.trace(pos, d, image_width=wdt)]
+        for a, b in zip(base, out):
+            assert np.array_equal(a, b, equal_nan=True), f"image_width {wdt}"
     # SoA planes + a random queue order
     soa_in = torch.cat([pos.t().contiguous(), d.t().contiguous()]).contiguous()  # [6, n]
     soa_out = torch.empty_like(soa_in)
