@@ -1,0 +1,124 @@
+"""GPU tests of the reference-shaped adapters (RRE / LIM / CAM call shapes) against the oracle."""
+import numpy as np
+import pytest
+
+from conftest import assert_parity, golden_kwargs, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def test_rre_call_shape_per_ray_and_batch():
+    from blackhole_geodesic_calculator_b200 import adapters
+    g = load_golden("rre_shape_16x16.npz")
+    kw = golden_kwargs(g)
+    gi = adapters.GeodesicIntegratorSchwarzschild(mass=kw["M"], time_like=False)
+    # batched body of spacetime_ray_cast (RRE.py:271-313): camera at `origin`, BH at bh_loc
+    bh = np.array([1.0, 2.0, 3.0])
+    origin = g["entry_pos"][0] + bh
+    hit, hit_bh, end_dir, end_loc = adapters.spacetime_ray_cast_batch(gi, origin, g["entry_dir"], bh_loc=bh,
+                                                                    curve_end=kw["lambda_max"])
+    assert not hit.any()
+    assert np.array_equal(hit_bh, g["status"] == 1)
+    ok = g["status"] == 3  # the normal RRE ending: affine length used up
+    assert np.abs(end_loc[ok] - g["exit_pos"][ok]).max() / 50.0 < 1e-6
+    assert np.abs(end_dir[ok] - g["exit_dir"][ok]).max() < 1e-6
+    # per-ray drop-in with the reference's return shape (RRE.py:293-297,307-308)
+    for i in (0, 17, 200):
+        k_xyz, x_xyz, result = gi.calc_trajectory(g["entry_dir"][i], g["entry_pos"][i], curve_end=kw["lambda_max"],
+                                                  nr_points_curve=10000)
+        assert result["start_inside_hole"] is False
+        assert result["hit_blackhole"] == bool(g["status"][i] == 1)
+        x, y, z = x_xyz
+        kx, ky, kz = k_xyz
+        end_loc_i = np.array([x[-1], y[-1], z[-1]])
+        end_dir_i = np.array([kx[-1], ky[-1], kz[-1]])
+        assert np.abs(end_loc_i - g["exit_pos"][i]).max() / 50.0 < 1e-6
+        assert np.abs(end_dir_i - g["exit_dir"][i]).max() < 1e-6
+    with pytest.raises(NotImplementedError):
+        adapters.GeodesicIntegratorSchwarzschild(time_like=True)
+
+
+def test_lim_call_shape_scaling_and_messages():
+    from blackhole_geodesic_calculator_b200 import adapters, raygen
+    from oracle import port
+    sw = adapters.SchwarzschildGeodesic(metric="schwarzschild")
+    ratio, r_obj = 30.0, 3.0            # a Blender sphere of radius 3 standing for 30 r_s (LIM.py:488)
+    pos, d = raygen.config_bundle(24, 24, 1, fov=0.5, r_sphere=60.0)
+    locs = pos / 60.0 * r_obj           # entry points on the Blender sphere, relative to its centre
+    end_loc, end_dir, hit_bh, outside, status = sw.ray_trace_batch(d, locs, exit_tolerance=0.2,
+                                                                   ratio_obj_to_blackhole=ratio)
+    o = port.trace(locs * (ratio / r_obj), d, M=0.5, r_sphere=ratio, lambda_max=sw.approximateCurveEnd(ratio))
+    assert np.array_equal(status, o["status"])
+    assert_parity(end_loc * (ratio / r_obj), end_dir, status, o["exit_pos"], o["exit_dir"], o["status"], ratio)
+    assert np.array_equal(hit_bh, o["status"] == 1) and not outside.any()
+    # exit points are back on the Blender sphere
+    assert np.abs(np.linalg.norm(end_loc[~hit_bh], axis=1) - r_obj).max() < 1e-9
+    # per-ray shape and the 'Outside' message when the affine length runs out (LIM.py:308-314)
+    x, y, z, el, ed, mes = sw.ray_trace(d[5], locs[5], ratio_obj_to_blackhole=ratio)
+    assert mes["hit_blackhole"] == bool(o["status"][5] == 1) and "error" not in mes
+    assert np.allclose(el, end_loc[5]) and len(x) == 2
+    x, y, z, el, ed, mes = sw.ray_trace(d[5], locs[5], ratio_obj_to_blackhole=ratio, curve_end=5.0)
+    assert mes.get("error") == "Outside" and mes["hit_blackhole"] is False
+
+
+def test_cam_call_shape():
+    from blackhole_geodesic_calculator_b200 import adapters, raygen
+    from oracle import port
+    cam = adapters.RelativisticCamera(resolution=[16, 24], field_of_view=[0.5, 0.5], M=1.0).run()
+    assert cam.ray_blackhole_hit.shape == (16, 24) and cam.ray_end.shape == (16, 24, 6)
+    d = raygen.camera_rays(24, 16, 1, 0.5, 0.5, cam.rotation, jitter="none")
+    p, hit = raygen.sphere_entry(cam.camera_location, d, 60.0)
+    assert hit.all()
+    o = port.trace(p, d)
+    assert np.array_equal(cam.ray_blackhole_hit.reshape(-1), (o["status"] == 1).astype(np.int64))
+    ok = o["status"] == 0
+    assert np.abs(cam.ray_end.reshape(-1, 6)[ok, 3:6] - o["exit_dir"][ok]).max() < 1e-6   # CAM.py:228 reads [3:6]
+    assert np.abs(cam.ray_end.reshape(-1, 6)[ok, 0:3] - o["exit_pos"][ok]).max() / 60.0 < 1e-6
+    # a camera that partly misses the sphere: missing rays keep their flat direction and status -1
+    cam2 = adapters.RelativisticCamera(resolution=[8, 8], field_of_view=[2.0, 2.0], M=1.0).run()
+    assert (cam2.ray_status == -1).any() and (cam2.ray_status >= 0).any()
+
+
+def test_trace_sharded_nccl_two_gpus():
+    """Interleaved sharding + NCCL gather on real devices (needs >= 2 GPUs; the gloo twin runs on CPU)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    import socket
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == ["none", "ok"]
+
+
+def _nccl_worker(rank, world, port, q):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from blackhole_geodesic_calculator_b200 import api, distributed, raygen
+        pos, d = raygen.config_bundle(64, 64, 1)
+        tp = torch.from_numpy(pos).cuda()
+        td = torch.from_numpy(d).cuda()
+        out = distributed.trace_sharded(tp, td, dst=0)
+        if rank == 0:
+            ref = api.trace(tp, td)
+            ok = all(torch.equal(a, b) for a, b in zip(out, ref))
+            q.put("ok" if ok else "mismatch")
+        else:
+            q.put("none" if out is None else "unexpected")
+    finally:
+        dist.destroy_process_group()
