@@ -87,6 +87,16 @@ __device__ __forceinline__ double inv_tenth_root(double a) {
     return x;
 }
 
+// max(|a|, |b|) on the integer pipe: for finite doubles the order of |x| is the order of its bit pattern.
+// (A NaN compares largest and propagates, which only ever turns an already-NaN error norm NaN.)
+__device__ __forceinline__ double abs_max(double a, double b) {
+    // written on the 32-bit halves so that the compiler cannot turn it back into FP64-pipe |x| operations
+    const int ha = __double2hiint(a) & 0x7fffffff, hb = __double2hiint(b) & 0x7fffffff;
+    const unsigned la = (unsigned)__double2loint(a), lb = (unsigned)__double2loint(b);
+    const bool a_ge = (ha > hb) || (ha == hb && la >= lb);
+    return __hiloint2double(a_ge ? ha : hb, (int)(a_ge ? la : lb));
+}
+
 // a^(1/5) for a in [1e-30, 1e30] (initial-step heuristic): Newton on x^-5 = a for the inverse root, then
 // a * x^4.  Float seed 1e-5 -> two steps -> 1e-18.
 __device__ __forceinline__ double fifth_root(double a) {
@@ -107,11 +117,16 @@ __device__ __forceinline__ double fifth_root(double a) {
 // ulp up to |th| ~ 1e9; beyond that (a state that has already blown up) the result is NaN, which the step
 // controller treats like any other non-finite error norm.
 __device__ __forceinline__ void sincos_tab(double th, double* s, double* c) {
-    const int n = __double2int_rn(th * TAB(T_TWO_OVER_PI));
-    const double dn = (double)n;
+    // n = rint(th * 2/pi) by the 1.5 * 2^52 trick: one FMA + one add, no FP64<->int conversion instructions
+    const double big = 6755399441055744.0;
+    const double tn = fma(th, TAB(T_TWO_OVER_PI), big);
+    const int n = __double2loint(tn);
+    const double dn = tn - big;
     double r = fma(-dn, TAB(T_PIO2_1), th);
     r = fma(-dn, TAB(T_PIO2_1T), r);
-    r = (fabs(th) < 1.0e9) ? r : __longlong_as_double(0x7ff8000000000000LL);
+    // |th| >= 1e9 (0x41CDCD65 in the high word), inf or NaN -> NaN; integer compare keeps it off the FP64 pipe
+    const bool ok = (unsigned)(__double2hiint(th) & 0x7fffffff) < 0x41CDCD65u;
+    r = ok ? r : __longlong_as_double(0x7ff8000000000000LL);
     const double z = r * r;
     double ps = fma(z, TAB(T_S6), TAB(T_S5));
     double pc = fma(z, TAB(T_C6), TAB(T_C5));
@@ -307,8 +322,8 @@ __device__ __forceinline__ double rk45_attempt(const double (&k)[NK], const doub
         g = fma(TAB(EA4), K[3][i], g);
         g = fma(TAB(EA5), K[4][i], g);
         ex[i] = fma(TAB(EA6), K[5][i], g) * h2;
-        sk[i] = fma(fmax(fabs(k[i]), fabs(kn[i])), rtol, atol);
-        sx[i] = fma(fmax(fabs(x[i]), fabs(xn[i])), rtol, atol);
+        sk[i] = fma(abs_max(k[i], kn[i]), rtol, atol);
+        sx[i] = fma(abs_max(x[i], xn[i]), rtol, atol);
     }
     // one reciprocal per group of four scales (two momentum/position pairs); scales are >= atol so the
     // products neither overflow nor underflow
