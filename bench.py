@@ -30,15 +30,20 @@ FLOP_FIXED, FLOP_PER_ATTEMPT = 230.0, 760.0  # FLOP(ray) = 230 +
 NOMINAL_FP64_TFLOPS = 37.2                   # 148 SM x 64 FMA/clk x 2 x 1.965 GHz
 
 
-def frame_rays(frame_index: int, width=W, height=H, spp=SPP, first=0, count=None):
-    """Entry positions/directions of one frame of the orbiting-camera animation (config 4; frame 0 = config 2)."""
+def frame_camera_pos(frame_index: int):
+    """Camera position of animation frame `frame_index` (config 4: azimuth += 3.6 deg per frame; frame 0 = config 2)."""
     from blackhole_geodesic_calculator_b200 import raygen
     az = math.radians(3.6 * frame_index)
     c0 = np.array(raygen.CFG_CAMERA_POS)
     ca, sa = math.cos(az), math.sin(az)
-    cam = np.array([ca * c0[0] - sa * c0[1], sa * c0[0] + ca * c0[1], c0[2]])
-    return raygen.config_bundle(width, height, spp, jitter="philox", cam_pos=tuple(cam), first_ray=first,
-                                n_rays=count)
+    return (ca * c0[0] - sa * c0[1], sa * c0[0] + ca * c0[1], c0[2])
+
+
+def frame_rays(frame_index: int, width=W, height=H, spp=SPP, first=0, count=None):
+    """Entry positions/directions of one frame of the orbiting-camera animation (host generator)."""
+    from blackhole_geodesic_calculator_b200 import raygen
+    return raygen.config_bundle(width, height, spp, jitter="philox", cam_pos=frame_camera_pos(frame_index),
+                                first_ray=first, n_rays=count)
 
 
 class ClockSampler:
@@ -55,7 +60,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -249,10 +254,31 @@ def run_b200(args):
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
 
-    t = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    # end-to-end from the camera description: ~150 bytes in, rays generated on the device,
+    # (a) all outputs, (b) directions + status only (what the RRE / CAM consumers read)
+    from blackhole_geodesic_calculator_b200 import raygen
+    cpos = frame_camera_pos(rank)
+    cam = api.make_camera(cpos, raygen.look_at_rotation(cpos), W, H * SPP, raygen.CFG_FOV, raygen.CFG_FOV,
+                          seed=raygen.CFG_SEED, jitter="philox")
+    # the s -> y -> x stack of SPP images is addressed as one image of H*SPP rows: same rays, same order
+    cam.height = H
+    cam_times = []
+    for want_pos in (True, False):
+        bufs = (pin_op if want_pos else None, pin_od, pin_st)
+        api.trace_camera(cam, n, mode=args.mode, refill_threshold=args.threshold, device=local, want_pos=want_pos,
+                         buffers=bufs)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            api.trace_camera(cam, n, mode=args.mode, refill_threshold=args.threshold, device=local,
+                             want_pos=want_pos, buffers=bufs)
+        torch.cuda.synchronize(dev)
+        cam_times.append(time.perf_counter() - t0)
+
+    t = torch.tensor([total_ms, e2e_s * 1e3, cam_times[0] * 1e3, cam_times[1] * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms = float(t[0]), float(t[1])
+    total_ms, e2e_ms, cam_full_ms, cam_dir_ms = (float(v) for v in t)
     value = world * n * args.steps / (total_ms * 1e-3)
     e2e_value = world * n * e2e_steps / (e2e_ms * 1e-3)
 
@@ -263,6 +289,12 @@ def run_b200(args):
         except Exception:
             peak_tf, clk_est = None, None
         achieved_tf = flop_per_launch / (kavg * 1e-3) / 1e12
+        traffic = None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                traffic = json.load(f).get(args.mode, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
         peak = peak_tf or NOMINAL_FP64_TFLOPS
         line = {
             "metric": "geodesic rays/s (1024^2 x 5 spp Schwarzschild frame)", "value": value, "unit": "rays/s",
@@ -279,6 +311,12 @@ def run_b200(args):
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n * 48, "d2h_bytes_per_step": n * 52,
                     "steps": e2e_steps, "api": "bhg_trace_schwarzschild_f64_host (pinned numpy in/out, chunked "
                                                "H2D/trace/D2H pipeline)"},
+            "e2e_camera": {"all_outputs": {"value": world * n * e2e_steps / (cam_full_ms * 1e-3), "unit": "rays/s",
+                                           "h2d_bytes_per_step": 176, "d2h_bytes_per_step": n * 52},
+                           "dir_and_status": {"value": world * n * e2e_steps / (cam_dir_ms * 1e-3), "unit": "rays/s",
+                                              "h2d_bytes_per_step": 176, "d2h_bytes_per_step": n * 28},
+                           "api": "bhg_trace_camera_f64_host: rays generated on the device from the camera struct "
+                                  "(next-row 1), pinned numpy outputs"},
             "gpu_launches": int(launches),
             "kernel_ms": {"mean": kavg, "min": float(np.min(kern_ms)), "max": float(np.max(kern_ms))},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",
@@ -288,7 +326,8 @@ def run_b200(args):
                          "frac_of_nominal": achieved_tf / NOMINAL_FP64_TFLOPS,
                          "algorithmic_flop_per_launch": flop_per_launch,
                          "hbm_gbs_achieved": n * 100 / (kavg * 1e-3) / 1e9,
-                         "traffic": None, "dfma_clock_mhz_est": clk_est},
+                         "traffic": traffic, "traffic_unit": "bytes/launch (ncu dram read+write, profiles/ncu_traffic.json)",
+                         "algorithmic_bytes_per_launch": n * 100, "dfma_clock_mhz_est": clk_est},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -316,7 +355,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="parity", choices=["parity", "plane"])

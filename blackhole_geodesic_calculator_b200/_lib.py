@@ -30,6 +30,22 @@ class BhgParams(ctypes.Structure):
     ]
 
 
+class BhgCamera(ctypes.Structure):
+    """Mirror of `struct bhg_camera` (include/bhgeo.h)."""
+    _fields_ = [
+        ("origin", ctypes.c_double * 3),
+        ("rotation", ctypes.c_double * 9),
+        ("fov_x", ctypes.c_double),
+        ("fov_y", ctypes.c_double),
+        ("first_ray", ctypes.c_int64),
+        ("seed", ctypes.c_uint64),
+        ("width", ctypes.c_int32),
+        ("height", ctypes.c_int32),
+        ("jitter", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
 class BhgError(RuntimeError):
     def __init__(self, code, message):
         super().__init__(f"bhgeo error {code}: {message}")
@@ -44,6 +60,12 @@ _SIGNATURES = {
                                                    ctypes.POINTER(BhgParams), ctypes.c_int32, _P]),
     "bhg_trace_schwarzschild_f64_host": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, ctypes.c_int64,
                                                         ctypes.POINTER(BhgParams), ctypes.c_int32]),
+    "bhg_generate_rays_f64": (ctypes.c_int, [ctypes.POINTER(BhgCamera), ctypes.c_double, ctypes.c_int64, _P, _P, _P,
+                                             ctypes.c_int32, _P]),
+    "bhg_trace_camera_f64": (ctypes.c_int, [ctypes.POINTER(BhgCamera), _P, _P, _P, _P, ctypes.c_int64,
+                                            ctypes.POINTER(BhgParams), ctypes.c_int32, _P]),
+    "bhg_trace_camera_f64_host": (ctypes.c_int, [ctypes.POINTER(BhgCamera), _P, _P, _P, _P, ctypes.c_int64,
+                                                 ctypes.POINTER(BhgParams), ctypes.c_int32]),
     "bhg_host_alloc": (_P, [ctypes.c_int64]),
     "bhg_host_free": (None, [_P]),
     "bhg_sum_counters": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int32, _P,

@@ -153,7 +153,7 @@ class RelativisticCamera:
         n = d.shape[0]
         exit_pos = np.full((n, 3), np.nan)
         exit_dir = d.copy()                      # rays that miss the sphere keep their flat direction
-        status = np.full(n, -1, dtype=np.int32)  # -1: never entered the curved region
+        status = np.full(n, api.MISSED_SPHERE, dtype=np.int32)  # never entered the curved region
         if hit.any():
             ep, ed, st = api.trace(p[hit], d[hit], self.M, self.r_sphere, max_step=self.max_step, mode=mode,
                                    device=self.device)

@@ -19,10 +19,11 @@ import math
 import numpy as np
 
 from . import _lib
-from ._lib import BhgParams
+from ._lib import BhgCamera, BhgParams
 
-ESCAPED, CAPTURED, START_INSIDE_HOLE, LAMBDA_EXHAUSTED, STEP_FAILED = 0, 1, 2, 3, 4
-STATUS_NAMES = {0: "ESCAPED", 1: "CAPTURED", 2: "START_INSIDE_HOLE", 3: "LAMBDA_EXHAUSTED", 4: "STEP_FAILED"}
+ESCAPED, CAPTURED, START_INSIDE_HOLE, LAMBDA_EXHAUSTED, STEP_FAILED, MISSED_SPHERE = 0, 1, 2, 3, 4, 5
+STATUS_NAMES = {0: "ESCAPED", 1: "CAPTURED", 2: "START_INSIDE_HOLE", 3: "LAMBDA_EXHAUSTED", 4: "STEP_FAILED",
+                5: "MISSED_SPHERE"}
 MODES = {"parity": 0, "plane": 1}
 LAYOUT_SOA, LAYOUT_AOS = 0, 1
 
@@ -106,6 +107,77 @@ def trace_device(in_ptr, in_dir_ptr, out_ptr, out_dir_ptr, status_ptr, counters_
     _lib.check(lib.bhg_trace_schwarzschild_f64(in_ptr, in_dir_ptr, out_ptr, out_dir_ptr, status_ptr, counters_ptr,
                                                order_ptr, int(n), int(layout), ctypes.byref(params), int(device),
                                                stream or None))
+
+
+def make_camera(origin, rotation, width, height, fov_x=0.6, fov_y=0.6, seed=42, jitter="philox", first_ray=0):
+    """`struct bhg_camera` for the fused generate+trace entry points: the pinhole camera of the reference's
+    render loop (RelativisticRenderEngine.py:181-189,223-230).  `origin` is relative to the black-hole centre,
+    `rotation` the 3x3 camera-to-world matrix (raygen.look_at_rotation / euler_xyz_rotation)."""
+    if jitter not in ("none", "philox"):
+        raise ValueError("device-side generation supports jitter 'none' or 'philox' (the MT19937 stream of the "
+                         "reference is sequential; use raygen.camera_rays for it)")
+    cam = BhgCamera()
+    cam.origin[:] = [float(v) for v in origin]
+    cam.rotation[:] = [float(v) for v in np.asarray(rotation, dtype=np.float64).reshape(9)]
+    cam.fov_x, cam.fov_y = float(fov_x), float(fov_y)
+    cam.first_ray, cam.seed = int(first_ray), int(seed)
+    cam.width, cam.height = int(width), int(height)
+    cam.jitter, cam.reserved = (1 if jitter == "philox" else 0), 0
+    return cam
+
+
+def generate_rays(cam: BhgCamera, n, r_sphere, device=0):
+    """Device-side primary rays: torch CUDA tensors (entry_pos[n,3], entry_dir[n,3], hit[n] int32: 0 or 5)."""
+    import torch
+
+    dev = torch.device("cuda", device)
+    pos = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    d = torch.empty((n, 3), dtype=torch.float64, device=dev)
+    hit = torch.empty(n, dtype=torch.int32, device=dev)
+    _lib.check(_lib.load().bhg_generate_rays_f64(ctypes.byref(cam), float(r_sphere), int(n), pos.data_ptr(),
+                                                 d.data_ptr(), hit.data_ptr(), int(device),
+                                                 torch.cuda.current_stream(dev).cuda_stream or None))
+    return pos, d, hit
+
+
+def trace_camera(cam: BhgCamera, n, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, *, max_step=math.inf,
+                 eps_horizon=0.01, lambda_max=None, mode="parity", refill_threshold=0, device=0, want_pos=True,
+                 return_counters=False, out="numpy", buffers=None):
+    """Fused device-side ray generation + trace of `n` rays of `cam` (one frame or tile from ~150 bytes of input).
+
+    out="numpy": host arrays (through bhg_trace_camera_f64_host; `buffers` may supply pre-allocated, e.g. pinned,
+    (exit_pos|None, exit_dir, status) arrays).  out="torch": CUDA tensors on `device`, asynchronous.
+    want_pos=False skips the exit positions (directions + status are what the RRE / CAM consumers read).
+    Returns (exit_pos or None, exit_dir, status[, counters])."""
+    params = make_params(M, r_sphere, rtol, atol, max_step, eps_horizon, lambda_max, mode, refill_threshold)
+    lib = _lib.load()
+    n = int(n)
+    if out == "torch":
+        import torch
+
+        dev = torch.device("cuda", device)
+        ep = torch.empty((n, 3), dtype=torch.float64, device=dev) if want_pos else None
+        ed = torch.empty((n, 3), dtype=torch.float64, device=dev)
+        st = torch.empty(n, dtype=torch.int32, device=dev)
+        cnt = torch.empty((2, n), dtype=torch.int32, device=dev) if return_counters else None
+        _lib.check(lib.bhg_trace_camera_f64(ctypes.byref(cam), ep.data_ptr() if want_pos else None, ed.data_ptr(),
+                                            st.data_ptr(), cnt.data_ptr() if return_counters else None, n,
+                                            ctypes.byref(params), int(device),
+                                            torch.cuda.current_stream(dev).cuda_stream or None))
+    else:
+        if buffers is not None:
+            ep, ed, st = buffers
+        else:
+            ep = np.empty((n, 3), dtype=np.float64) if want_pos else None
+            ed = np.empty((n, 3), dtype=np.float64)
+            st = np.empty(n, dtype=np.int32)
+        cnt = np.empty((2, n), dtype=np.int32) if return_counters else None
+        p = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+        _lib.check(lib.bhg_trace_camera_f64_host(ctypes.byref(cam), p(ep) if want_pos else None, p(ed), p(st), p(cnt),
+                                                 n, ctypes.byref(params), int(device)))
+    if return_counters:
+        return ep, ed, st, cnt
+    return ep, ed, st
 
 
 def sum_counters(counters_ptr, status_ptr, n, device=0, stream=0):

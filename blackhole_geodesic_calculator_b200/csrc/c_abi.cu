@@ -47,7 +47,7 @@ struct DeviceCtx {
     std::mutex mu;
     bool ready = false;
     int sm_count = 0;
-    int blocks_per_sm[2][2] = {{0, 0}, {0, 0}};  // [mode][layout]
+    int blocks_per_sm[2][3] = {{0, 0, 0}, {0, 0, 0}};  // [mode][input kind]
     unsigned long long* queue_slots = nullptr;   // kQueueSlots work-queue heads
     std::atomic<unsigned> next_slot{0};
     // staging buffers of the host entry point (grow-only)
@@ -60,9 +60,9 @@ struct DeviceCtx {
 
 DeviceCtx g_ctx[kMaxDevices];
 
-template <int NK, bool AOS>
+template <int NK, int IN>
 int query_occupancy(int* out) {
-    BHG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, bhg::trace_kernel<NK, AOS>, 128, 0));
+    BHG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, bhg::trace_kernel<NK, IN>, 128, 0));
     return 0;
 }
 
@@ -85,10 +85,12 @@ int ensure_device(int device, DeviceCtx** out) {
                         prop.major, prop.minor);
         c.sm_count = prop.multiProcessorCount;
         int rc;
-        if ((rc = query_occupancy<4, false>(&c.blocks_per_sm[0][0]))) return rc;
-        if ((rc = query_occupancy<4, true>(&c.blocks_per_sm[0][1]))) return rc;
-        if ((rc = query_occupancy<3, false>(&c.blocks_per_sm[1][0]))) return rc;
-        if ((rc = query_occupancy<3, true>(&c.blocks_per_sm[1][1]))) return rc;
+        if ((rc = query_occupancy<4, bhg::IN_SOA>(&c.blocks_per_sm[0][0]))) return rc;
+        if ((rc = query_occupancy<4, bhg::IN_AOS>(&c.blocks_per_sm[0][1]))) return rc;
+        if ((rc = query_occupancy<4, bhg::IN_CAMERA>(&c.blocks_per_sm[0][2]))) return rc;
+        if ((rc = query_occupancy<3, bhg::IN_SOA>(&c.blocks_per_sm[1][0]))) return rc;
+        if ((rc = query_occupancy<3, bhg::IN_AOS>(&c.blocks_per_sm[1][1]))) return rc;
+        if ((rc = query_occupancy<3, bhg::IN_CAMERA>(&c.blocks_per_sm[1][2]))) return rc;
         BHG_CUDA(cudaMalloc(&c.queue_slots, kQueueSlots * sizeof(unsigned long long)));
         BHG_CUDA(cudaMalloc(&c.totals, 3 * sizeof(long long)));
         c.ready = true;
@@ -118,11 +120,30 @@ int validate(const bhg_params* p, long long n) {
     return 0;
 }
 
+int convert_camera(const bhg_camera* cam, double r_sphere, bhg::Camera* out) {
+    if (!cam) return fail(BHG_ERR_INVALID_ARGUMENT, "camera is NULL");
+    if (cam->width <= 0 || cam->height <= 0) return fail(BHG_ERR_INVALID_ARGUMENT, "camera width/height must be > 0");
+    if (cam->first_ray < 0 || cam->reserved != 0 || (cam->jitter != 0 && cam->jitter != 1))
+        return fail(BHG_ERR_INVALID_ARGUMENT, "camera first_ray must be >= 0, jitter 0 or 1, reserved 0");
+    if (!std::isfinite(r_sphere)) return fail(BHG_ERR_INVALID_ARGUMENT, "camera entry needs a finite r_sphere");
+    for (int i = 0; i < 3; i++) out->origin[i] = cam->origin[i];
+    for (int i = 0; i < 9; i++) out->rot[i] = cam->rotation[i];
+    out->fov_x = cam->fov_x; out->fov_y = cam->fov_y;
+    out->r_sphere = r_sphere;
+    out->first_ray = cam->first_ray;
+    out->seed = cam->seed;
+    out->width = cam->width; out->height = cam->height;
+    out->jitter = cam->jitter;
+    return 0;
+}
+
+// in_kind: bhg::IN_SOA / IN_AOS / IN_CAMERA (cam != nullptr)
 int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* out, double* out_dir, int32_t* status,
-                 int32_t* counters, const int32_t* order, long long n, int layout, const bhg_params* p,
-                 cudaStream_t stream) {
+                 int32_t* counters, const int32_t* order, long long n, int in_kind, const bhg::Camera* cam,
+                 const bhg_params* p, cudaStream_t stream) {
     if (n == 0) return 0;
     bhg::TraceArgs a;
+    memset(&a, 0, sizeof(a));
     a.in = in; a.in_dir = in_dir; a.out = out; a.out_dir = out_dir;
     a.status = status; a.counters = counters; a.order = order;
     a.n = n;
@@ -133,24 +154,44 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
     a.rtol = p->rtol; a.atol = p->atol; a.max_step = p->max_step;
     a.lambda_max = p->lambda_max > 0.0 ? p->lambda_max : 10.0 * p->r_sphere;
     a.refill_threshold = p->refill_threshold > 0 ? p->refill_threshold : 32;
-    a.tile_width = (p->image_width > 0 && p->image_width % 8 == 0 && n % (4LL * p->image_width) == 0 && !order)
-                       ? p->image_width : 0;
+    int image_width = p->image_width;
+    if (cam) {
+        a.cam = *cam;
+        // tiles must not straddle the call's first ray: only when the call starts on a 4-row band boundary
+        image_width = (cam->first_ray % (4LL * cam->width) == 0) ? cam->width : 0;
+    }
+    a.tile_width = (image_width > 0 && image_width % 8 == 0 && n % (4LL * image_width) == 0 && !order) ? image_width : 0;
     unsigned slot = c.next_slot.fetch_add(1) % kQueueSlots;
     a.queue_head = c.queue_slots + slot;
     BHG_CUDA(cudaMemsetAsync(a.queue_head, 0, sizeof(unsigned long long), stream));
-    const int mode = p->mode, aos = layout == BHG_LAYOUT_AOS ? 1 : 0;
+    const int mode = p->mode;
     long long want_blocks = (n + 127) / 128;
-    long long max_blocks = (long long)c.sm_count * c.blocks_per_sm[mode][aos];
+    long long max_blocks = (long long)c.sm_count * c.blocks_per_sm[mode][in_kind];
     int blocks = (int)(want_blocks < max_blocks ? want_blocks : max_blocks);
     if (mode == BHG_MODE_PARITY) {
-        if (aos) bhg::trace_kernel<4, true><<<blocks, 128, 0, stream>>>(a);
-        else bhg::trace_kernel<4, false><<<blocks, 128, 0, stream>>>(a);
+        if (in_kind == bhg::IN_CAMERA) bhg::trace_kernel<4, bhg::IN_CAMERA><<<blocks, 128, 0, stream>>>(a);
+        else if (in_kind == bhg::IN_AOS) bhg::trace_kernel<4, bhg::IN_AOS><<<blocks, 128, 0, stream>>>(a);
+        else bhg::trace_kernel<4, bhg::IN_SOA><<<blocks, 128, 0, stream>>>(a);
     } else {
-        if (aos) bhg::trace_kernel<3, true><<<blocks, 128, 0, stream>>>(a);
-        else bhg::trace_kernel<3, false><<<blocks, 128, 0, stream>>>(a);
+        if (in_kind == bhg::IN_CAMERA) bhg::trace_kernel<3, bhg::IN_CAMERA><<<blocks, 128, 0, stream>>>(a);
+        else if (in_kind == bhg::IN_AOS) bhg::trace_kernel<3, bhg::IN_AOS><<<blocks, 128, 0, stream>>>(a);
+        else bhg::trace_kernel<3, bhg::IN_SOA><<<blocks, 128, 0, stream>>>(a);
     }
     g_launches.fetch_add(1);
     BHG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int ensure_stage(DeviceCtx* c, size_t need) {
+    if (c->stage_bytes < need) {
+        if (c->stage) cudaFree(c->stage);
+        c->stage = nullptr;
+        c->stage_bytes = 0;
+        BHG_CUDA(cudaMalloc(&c->stage, need));
+        c->stage_bytes = need;
+    }
+    for (auto& s : c->streams)
+        if (!s) BHG_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     return 0;
 }
 
@@ -184,7 +225,8 @@ int bhg_trace_schwarzschild_f64(const double* in, const double* in_dir, double* 
         return fail(BHG_ERR_INVALID_ARGUMENT, "AOS layout needs in_dir and out_dir");
     DeviceCtx* c;
     if ((rc = ensure_device(device, &c))) return rc;
-    return launch_trace(*c, in, in_dir, out, out_dir, status, counters, order, n, layout, params, (cudaStream_t)stream);
+    return launch_trace(*c, in, in_dir, out, out_dir, status, counters, order, n,
+                        layout == BHG_LAYOUT_AOS ? bhg::IN_AOS : bhg::IN_SOA, nullptr, params, (cudaStream_t)stream);
 }
 
 int bhg_trace_schwarzschild_f64_host(const double* entry_pos, const double* entry_dir, double* exit_pos,
@@ -201,15 +243,7 @@ int bhg_trace_schwarzschild_f64_host(const double* entry_pos, const double* entr
     // device staging: pos_in | dir_in | pos_out | dir_out | status | counters
     const size_t vec = (size_t)n * 3 * sizeof(double);
     const size_t need = 4 * vec + (size_t)n * 3 * sizeof(int32_t) + 1024;
-    if (c->stage_bytes < need) {
-        if (c->stage) cudaFree(c->stage);
-        c->stage = nullptr;
-        c->stage_bytes = 0;
-        BHG_CUDA(cudaMalloc(&c->stage, need));
-        c->stage_bytes = need;
-    }
-    for (auto& s : c->streams)
-        if (!s) BHG_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    if ((rc = ensure_stage(c, need))) return rc;
     char* base = (char*)c->stage;
     double* d_pin = (double*)base;
     double* d_din = (double*)(base + vec);
@@ -233,9 +267,83 @@ int bhg_trace_schwarzschild_f64_host(const double* entry_pos, const double* entr
         // writing attempts/accepted into a 2m block and scattering on the way back
         int32_t* cnt_chunk = counters ? d_cnt + 2 * b : nullptr;
         rc = launch_trace(*c, d_pin + 3 * b, d_din + 3 * b, d_pout + 3 * b, d_dout + 3 * b, d_status + b, cnt_chunk,
-                          nullptr, m, BHG_LAYOUT_AOS, params, s);
+                          nullptr, m, bhg::IN_AOS, nullptr, params, s);
         if (rc) return rc;
         BHG_CUDA(cudaMemcpyAsync(exit_pos + 3 * b, d_pout + 3 * b, (size_t)m * 24, cudaMemcpyDeviceToHost, s));
+        BHG_CUDA(cudaMemcpyAsync(exit_dir + 3 * b, d_dout + 3 * b, (size_t)m * 24, cudaMemcpyDeviceToHost, s));
+        BHG_CUDA(cudaMemcpyAsync(status + b, d_status + b, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+        if (counters) {
+            BHG_CUDA(cudaMemcpyAsync(counters + b, cnt_chunk, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+            BHG_CUDA(cudaMemcpyAsync(counters + n + b, cnt_chunk + m, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    for (auto& s : c->streams) BHG_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int bhg_generate_rays_f64(const bhg_camera* cam, double r_sphere, int64_t n, double* pos, double* dir, int32_t* hit,
+                          int32_t device, void* stream) {
+    bhg::Camera dc;
+    int rc = convert_camera(cam, r_sphere, &dc);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!pos || !dir))) return fail(BHG_ERR_INVALID_ARGUMENT, "bad n or NULL ray buffer");
+    DeviceCtx* c;
+    if ((rc = ensure_device(device, &c))) return rc;
+    if (n == 0) return 0;
+    long long blocks = (n + 255) / 256;
+    if (blocks > c->sm_count * 16LL) blocks = c->sm_count * 16LL;
+    bhg::generate_rays_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(dc, n, pos, dir, hit);
+    g_launches.fetch_add(1);
+    BHG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int bhg_trace_camera_f64(const bhg_camera* cam, double* exit_pos, double* exit_dir, int32_t* status,
+                         int32_t* counters, int64_t n, const bhg_params* params, int32_t device, void* stream) {
+    int rc = validate(params, n);
+    if (rc) return rc;
+    bhg::Camera dc;
+    if ((rc = convert_camera(cam, params->r_sphere, &dc))) return rc;
+    if (n > 0 && (!exit_dir || !status)) return fail(BHG_ERR_INVALID_ARGUMENT, "NULL output buffer");
+    DeviceCtx* c;
+    if ((rc = ensure_device(device, &c))) return rc;
+    return launch_trace(*c, nullptr, nullptr, exit_pos, exit_dir, status, counters, nullptr, n, bhg::IN_CAMERA, &dc,
+                        params, (cudaStream_t)stream);
+}
+
+int bhg_trace_camera_f64_host(const bhg_camera* cam, double* exit_pos, double* exit_dir, int32_t* status,
+                              int32_t* counters, int64_t n, const bhg_params* params, int32_t device) {
+    int rc = validate(params, n);
+    if (rc) return rc;
+    bhg::Camera dc;
+    if ((rc = convert_camera(cam, params->r_sphere, &dc))) return rc;
+    if (n > 0 && (!exit_dir || !status)) return fail(BHG_ERR_INVALID_ARGUMENT, "NULL output buffer");
+    DeviceCtx* c;
+    if ((rc = ensure_device(device, &c))) return rc;
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(c->host_mu);
+    const size_t vec = (size_t)n * 3 * sizeof(double);
+    if ((rc = ensure_stage(c, 2 * vec + (size_t)n * 3 * sizeof(int32_t) + 1024))) return rc;
+    char* base = (char*)c->stage;
+    double* d_pout = (double*)base;
+    double* d_dout = (double*)(base + vec);
+    int32_t* d_status = (int32_t*)(base + 2 * vec);
+    int32_t* d_cnt = d_status + n;
+    // chunks are whole 4-row bands so that every chunk keeps the 8 x 4 tile scheduling
+    const long long band = 4LL * cam->width;
+    long long chunk = n <= (1 << 16) ? n : (n <= (1 << 20) ? (n + 3) / 4 : (1 << 18));
+    if (n > chunk) chunk = ((chunk + band - 1) / band) * band;
+    int si = 0;
+    for (long long b = 0; b < n; b += chunk, si = (si + 1) % 3) {
+        const long long m = (n - b < chunk) ? (n - b) : chunk;
+        cudaStream_t s = c->streams[si];
+        bhg::Camera cc = dc;
+        cc.first_ray = dc.first_ray + b;
+        int32_t* cnt_chunk = counters ? d_cnt + 2 * b : nullptr;
+        rc = launch_trace(*c, nullptr, nullptr, exit_pos ? d_pout + 3 * b : nullptr, d_dout + 3 * b, d_status + b,
+                          cnt_chunk, nullptr, m, bhg::IN_CAMERA, &cc, params, s);
+        if (rc) return rc;
+        if (exit_pos) BHG_CUDA(cudaMemcpyAsync(exit_pos + 3 * b, d_pout + 3 * b, (size_t)m * 24, cudaMemcpyDeviceToHost, s));
         BHG_CUDA(cudaMemcpyAsync(exit_dir + 3 * b, d_dout + 3 * b, (size_t)m * 24, cudaMemcpyDeviceToHost, s));
         BHG_CUDA(cudaMemcpyAsync(status + b, d_status + b, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
         if (counters) {

@@ -15,6 +15,7 @@
 // always executed with all running lanes converged.
 #pragma once
 #include "geodesic_core.cuh"
+#include "raygen.cuh"
 
 namespace bhg {
 
@@ -32,7 +33,12 @@ struct TraceArgs {
     int has_outer;
     int refill_threshold;
     int tile_width;  // > 0: queue slots enumerate 8 x 4 pixel tiles of a row-major image of this width
+    Camera cam;      // IN_CAMERA only: rays are generated in the kernel, nothing is read from HBM
 };
+
+// where a ray's entry state comes from
+constexpr int IN_SOA = 0, IN_AOS = 1, IN_CAMERA = 2;
+constexpr int MISSED_SPHERE = 5;  // camera ray that never enters the sphere of influence (IN_CAMERA only)
 
 // queue slot -> ray index.  With the image hint, 32 consecutive slots (one warp's fetch when it starts empty)
 // cover an 8 x 4 pixel tile, whose rays have far more similar step counts than 32 pixels of one row.
@@ -53,9 +59,12 @@ constexpr int PEND_H = -2;   // horizon event active in the last step
 constexpr int PEND_E = -3;   // outer-sphere event active
 constexpr int PEND_HE = -5;  // both
 
-template <bool AOS>
-__device__ __forceinline__ void load_ray(const TraceArgs& a, long long idx, double (&x)[3], double (&k)[3]) {
-    if (AOS) {
+// returns false only for a camera ray that misses the sphere (k then holds its flat direction)
+template <int IN>
+__device__ __forceinline__ bool load_ray(const TraceArgs& a, long long idx, double (&x)[3], double (&k)[3]) {
+    if (IN == IN_CAMERA) {
+        return camera_ray(a.cam, idx, x, k);
+    } else if (IN == IN_AOS) {
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             x[c] = __ldg(a.in + 3 * idx + c);
@@ -68,15 +77,17 @@ __device__ __forceinline__ void load_ray(const TraceArgs& a, long long idx, doub
             k[c] = __ldg(a.in + (3 + c) * a.n + idx);
         }
     }
+    return true;
 }
 
-template <bool AOS>
+// outputs are AoS for IN_AOS / IN_CAMERA (exit positions optional: a.out may be NULL), planes for IN_SOA
+template <int IN>
 __device__ __forceinline__ void store_ray(const TraceArgs& a, long long idx, const double (&x)[3],
                                           const double (&k)[3], int status, int n_attempt, int n_accept) {
-    if (AOS) {
+    if (IN != IN_SOA) {
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            a.out[3 * idx + c] = x[c];
+            if (a.out) a.out[3 * idx + c] = x[c];
             a.out_dir[3 * idx + c] = k[c];
         }
     } else {
@@ -208,7 +219,7 @@ __device__ __forceinline__ bool all_finite(const double (&k)[NK], const double (
 #define BHG_MIN_BLOCKS 4
 #endif
 
-template <int NK, bool AOS>
+template <int NK, int IN>
 __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceArgs a) {
     constexpr int IR = 1;  // index of r in x
     constexpr unsigned FULL = 0xffffffffu;
@@ -269,15 +280,21 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
                     t = fma(s, h, t);
                 }
                 double x0[3] = {0, 0, 0}, k0[3] = {0, 0, 0}, xo[3], ko[3];
-                if (NK == 3) load_ray<AOS>(a, idx, x0, k0);
+                if (NK == 3 || final_status == MISSED_SPHERE) load_ray<IN>(a, idx, x0, k0);
                 if (final_status == START_INSIDE_HOLE) {
 #pragma unroll
                     for (int c = 0; c < 3; c++) xo[c] = ko[c] = __longlong_as_double(0x7ff8000000000000LL);
+                } else if (final_status == MISSED_SPHERE) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        xo[c] = __longlong_as_double(0x7ff8000000000000LL);
+                        ko[c] = k0[c];  // the ray continues in flat space with its original direction
+                    }
                 } else {
                     if (!all_finite<NK>(k, x)) final_status = STEP_FAILED;
                     exit_state<NK>(k, x, x0, k0, xo, ko);
                 }
-                store_ray<AOS>(a, idx, xo, ko, final_status, n_attempt, n_accept);
+                store_ray<IN>(a, idx, xo, ko, final_status, n_attempt, n_accept);
                 state = LANE_EMPTY;
             }
             // ---------------- refill idle lanes ----------------
@@ -293,12 +310,14 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
                     if (slot < a.n) {
                         idx = slot_to_ray(a, slot);
                         double x0[3], k0[3];
-                        load_ray<AOS>(a, idx, x0, k0);
+                        const bool enters = load_ray<IN>(a, idx, x0, k0);
                         n_attempt = 0;
                         n_accept = 0;
                         rejected = false;
                         t = 0.0;
-                        if (!init_state<NK>(x0, k0, a.rs, a.r_hor, k, x)) {
+                        if (!enters) {
+                            state = MISSED_SPHERE;
+                        } else if (!init_state<NK>(x0, k0, a.rs, a.r_hor, k, x)) {
                             state = START_INSIDE_HOLE;
                         } else if (!all_finite<NK>(k, x)) {
                             state = STEP_FAILED;  // singular entry (on the polar axis): scipy refuses such a y0
@@ -359,6 +378,21 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
                 }
             }
         }
+    }
+}
+
+// Standalone generator: entry positions / directions of n camera rays as AoS [n][3] (+ hit flag 0 / MISSED_SPHERE)
+__global__ void generate_rays_kernel(const Camera cam, long long n, double* __restrict__ pos, double* __restrict__ dir,
+                                     int32_t* __restrict__ hit) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double p[3], d[3];
+        const bool ok = camera_ray(cam, i, p, d);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            pos[3 * i + c] = ok ? p[c] : __longlong_as_double(0x7ff8000000000000LL);
+            dir[3 * i + c] = d[c];
+        }
+        if (hit) hit[i] = ok ? 0 : MISSED_SPHERE;
     }
 }
 

@@ -31,7 +31,10 @@ enum bhg_status {
     BHG_START_INSIDE_HOLE = 2, /* entry radius <= r_s + eps_horizon: result['start_inside_hole'] (RRE.py:296) */
     BHG_LAMBDA_EXHAUSTED = 3,  /* affine length lambda_max reached first: mes['error']=='Outside' (LIM.py:311-312);
                                   the normal ending of the RRE fixed-length call (RRE.py:293-294,307-308)   */
-    BHG_STEP_FAILED = 4        /* step size underflow / non-finite state (scipy status -1)                */
+    BHG_STEP_FAILED = 4,       /* step size underflow / non-finite state (scipy status -1)                */
+    BHG_MISSED_SPHERE = 5      /* camera entry points only: the primary ray never meets the sphere of influence
+                                  (the flat `scene.ray_cast` finds no "isBH" hit, LIM.py:224-237); exit_dir is
+                                  the unchanged flat direction, exit_pos is NaN                              */
 };
 
 enum bhg_error {
@@ -101,6 +104,40 @@ int bhg_trace_schwarzschild_f64(const double* in, const double* in_dir, double* 
 int bhg_trace_schwarzschild_f64_host(const double* entry_pos, const double* entry_dir, double* exit_pos,
                                      double* exit_dir, int32_t* status, int32_t* counters, int64_t n,
                                      const bhg_params* params, int32_t device);
+
+/* Pinhole camera of the reference's render loop: replaces the per-pixel direction construction of
+ * RelativisticRenderEngine.ray_trace (RRE.py:185-189,195-230: loop order s -> y -> x, pixel offsets, jitter,
+ * rotation by the camera matrix, normalisation) and the flat-space hit on the "isBH" sphere
+ * (LimitedRelativisticRenderEngine.py:224,265).  Ray i of a call is ray first_ray + i of that loop order.
+ * jitter = 1 draws the sub-pixel offsets from Philox-4x32-10(counter = ray index, key = seed), a counter-based
+ * stand-in for the reference's sequential random.random() stream (RRE.py:189,227). */
+typedef struct bhg_camera {
+    double origin[3];    /* camera position relative to the black-hole centre (RRE.py:278)       */
+    double rotation[9];  /* row-major camera-to-world rotation; camera looks along local -z       */
+    double fov_x, fov_y; /* field_of_view_x / _y (RRE.py:72-73,224-225)                           */
+    int64_t first_ray;
+    uint64_t seed;       /* sampling_seed (RRE.py:189)                                            */
+    int32_t width, height;
+    int32_t jitter;      /* 0: pixel centres, 1: Philox                                           */
+    int32_t reserved;    /* must be 0 */
+} bhg_camera;
+
+/* Generates n primary rays on the device: pos[n][3] = entry point on the sphere |p| = r_sphere (NaN if the ray
+ * misses), dir[n][3] = unit direction, hit[n] (NULL ok) = 0 or BHG_MISSED_SPHERE.  Device buffers. */
+int bhg_generate_rays_f64(const bhg_camera* cam, double r_sphere, int64_t n, double* pos, double* dir, int32_t* hit,
+                          int32_t device, void* stream);
+
+/* Fused generate + trace: the whole curved-spacetime part of one frame (or tile) from a 150-byte camera
+ * description; no ray buffer is read from memory.  Device output buffers, AoS [n][3]; exit_pos may be NULL when
+ * the consumer needs directions only (CamEdition.py:228 reads ray_end[...,3:6]; RRE.py:246 uses end_dir only).
+ * Rays that miss the sphere get BHG_MISSED_SPHERE.  params->image_width is set from the camera automatically. */
+int bhg_trace_camera_f64(const bhg_camera* cam, double* exit_pos, double* exit_dir, int32_t* status,
+                         int32_t* counters, int64_t n, const bhg_params* params, int32_t device, void* stream);
+
+/* Same with HOST output buffers (pinned or pageable): traces in chunks and overlaps the D2H of finished chunks
+ * with the integration of the next ones.  exit_pos and counters may be NULL. */
+int bhg_trace_camera_f64_host(const bhg_camera* cam, double* exit_pos, double* exit_dir, int32_t* status,
+                              int32_t* counters, int64_t n, const bhg_params* params, int32_t device);
 
 /* Pinned host memory for the staging path (optional convenience). */
 void* bhg_host_alloc(int64_t bytes);

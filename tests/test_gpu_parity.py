@@ -212,3 +212,54 @@ def test_error_codes_on_gpu(api):
     assert rc == -1
     rc = lib.bhg_trace_schwarzschild_f64(None, None, None, None, None, None, None, 0, 1, ctypes.byref(p), 63, None)
     assert rc == -3
+
+
+def test_device_raygen_matches_host_generator(api):
+    """device-side primary rays vs the host generator (same Philox stream, same order)."""
+    from blackhole_geodesic_calculator_b200 import raygen
+    rot = raygen.look_at_rotation(raygen.CFG_CAMERA_POS)
+    for (w, h, spp, jit) in ((64, 48, 2, "philox"), (40, 24, 1, "none")):
+        n = w * h * spp
+        cam = api.make_camera(raygen.CFG_CAMERA_POS, rot, w, h, 0.6, 0.6, seed=42, jitter=jit)
+        pos, d, hit = (t.cpu().numpy() for t in api.generate_rays(cam, n, 60.0))
+        hd = raygen.camera_rays(w, h, spp, 0.6, 0.6, rot, 42, jit)
+        hp, hhit = raygen.sphere_entry(raygen.CFG_CAMERA_POS, hd, 60.0)
+        assert np.array_equal(hit == 0, hhit)
+        assert np.abs(d - hd).max() < 4e-16                      # a few ulp (matmul summation order)
+        assert np.abs(pos[hhit] - hp[hhit]).max() / 60.0 < 1e-14
+    # a wide camera: some rays miss the sphere
+    cam = api.make_camera(raygen.CFG_CAMERA_POS, rot, 32, 32, 2.0, 2.0, jitter="none")
+    pos, d, hit = (t.cpu().numpy() for t in api.generate_rays(cam, 1024, 60.0))
+    assert (hit == 5).any() and (hit == 0).any() and np.isnan(pos[hit == 5]).all()
+    # first_ray offsets address the same stream
+    cam2 = api.make_camera(raygen.CFG_CAMERA_POS, rot, 32, 32, 2.0, 2.0, jitter="none", first_ray=500)
+    pos2, d2, hit2 = (t.cpu().numpy() for t in api.generate_rays(cam2, 524, 60.0))
+    assert np.array_equal(d2, d[500:]) and np.array_equal(hit2, hit[500:])
+
+
+def test_fused_camera_trace_equals_generate_then_trace(api):
+    """The fused kernel must give bit-identical results to generate_rays + trace, on host and device outputs,
+    with and without exit positions, including rays that miss the sphere."""
+    import torch
+    from blackhole_geodesic_calculator_b200 import raygen
+    from oracle import port
+    rot = raygen.look_at_rotation(raygen.CFG_CAMERA_POS)
+    for fov, w, h in ((0.6, 64, 64), (1.2, 48, 40)):
+        n = w * h
+        cam = api.make_camera(raygen.CFG_CAMERA_POS, rot, w, h, fov, fov, seed=7, jitter="philox")
+        pos, d, hit = api.generate_rays(cam, n, 60.0)
+        ok = (hit == 0).cpu().numpy()
+        ep0, ed0, st0 = (t.cpu().numpy() for t in api.trace(pos[hit == 0].contiguous(), d[hit == 0].contiguous()))
+        ep, ed, st, cnt = api.trace_camera(cam, n, return_counters=True)
+        assert np.array_equal(st[ok], st0) and (st[~ok] == 5).all()
+        assert np.array_equal(ep[ok], ep0) and np.array_equal(ed[ok], ed0)
+        assert np.isnan(ep[~ok]).all() and np.array_equal(ed[~ok], d.cpu().numpy()[~ok])
+        # directions only, torch outputs
+        _, ed_t, st_t = api.trace_camera(cam, n, want_pos=False, out="torch")
+        torch.cuda.synchronize()
+        assert np.array_equal(ed_t.cpu().numpy(), ed) and np.array_equal(st_t.cpu().numpy(), st)
+        # and against the oracle on the device-generated rays
+        o = port.trace(pos.cpu().numpy()[ok], d.cpu().numpy()[ok])
+        band = crit_band(pos.cpu().numpy()[ok], d.cpu().numpy()[ok], 1.0)
+        assert_parity(ep[ok], ed[ok], st[ok], o["exit_pos"], o["exit_dir"], o["status"], 60.0, exclude=band)
+        assert (cnt[0][ok][~band] == o["n_attempt"][~band]).mean() > 0.999
