@@ -275,10 +275,21 @@ def run_b200(args):
         torch.cuda.synchronize(dev)
         cam_times.append(time.perf_counter() - t0)
 
-    t = torch.tensor([total_ms, e2e_s * 1e3, cam_times[0] * 1e3, cam_times[1] * 1e3], dtype=torch.float64, device=dev)
+    # (c) camera -> sky-lookup coordinates (next-row 3): 12 B/ray come back
+    pin_uv = api.pinned_empty((n, 2), np.float32)
+    api.trace_camera_sky(cam, n, mode=args.mode, refill_threshold=args.threshold, device=local, buffers=(pin_uv, pin_st))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        api.trace_camera_sky(cam, n, mode=args.mode, refill_threshold=args.threshold, device=local,
+                             buffers=(pin_uv, pin_st))
+    torch.cuda.synchronize(dev)
+    cam_times.append(time.perf_counter() - t0)
+
+    t = torch.tensor([total_ms, e2e_s * 1e3] + [c * 1e3 for c in cam_times], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, cam_full_ms, cam_dir_ms = (float(v) for v in t)
+    total_ms, e2e_ms, cam_full_ms, cam_dir_ms, cam_uv_ms = (float(v) for v in t)
     value = world * n * args.steps / (total_ms * 1e-3)
     e2e_value = world * n * e2e_steps / (e2e_ms * 1e-3)
 
@@ -315,7 +326,9 @@ def run_b200(args):
                                            "h2d_bytes_per_step": 176, "d2h_bytes_per_step": n * 52},
                            "dir_and_status": {"value": world * n * e2e_steps / (cam_dir_ms * 1e-3), "unit": "rays/s",
                                               "h2d_bytes_per_step": 176, "d2h_bytes_per_step": n * 28},
-                           "api": "bhg_trace_camera_f64_host: rays generated on the device from the camera struct "
+                           "sky_uv_and_status": {"value": world * n * e2e_steps / (cam_uv_ms * 1e-3), "unit": "rays/s",
+                                                 "h2d_bytes_per_step": 176, "d2h_bytes_per_step": n * 12},
+                           "api": "bhg_trace_camera_f64_host / bhg_trace_camera_sky_host: rays generated on the device from the camera struct "
                                   "(next-row 1), pinned numpy outputs"},
             "gpu_launches": int(launches),
             "kernel_ms": {"mean": kavg, "min": float(np.min(kern_ms)), "max": float(np.max(kern_ms))},

@@ -66,6 +66,9 @@ _SIGNATURES = {
                                             ctypes.POINTER(BhgParams), ctypes.c_int32, _P]),
     "bhg_trace_camera_f64_host": (ctypes.c_int, [ctypes.POINTER(BhgCamera), _P, _P, _P, _P, ctypes.c_int64,
                                                  ctypes.POINTER(BhgParams), ctypes.c_int32]),
+    "bhg_sky_uv_f32": (ctypes.c_int, [_P, _P, ctypes.c_int64, _P, ctypes.c_int32, _P]),
+    "bhg_trace_camera_sky_host": (ctypes.c_int, [ctypes.POINTER(BhgCamera), _P, _P, ctypes.c_int64,
+                                                 ctypes.POINTER(BhgParams), ctypes.c_int32]),
     "bhg_host_alloc": (_P, [ctypes.c_int64]),
     "bhg_host_free": (None, [_P]),
     "bhg_sum_counters": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int32, _P,

@@ -180,6 +180,33 @@ def trace_camera(cam: BhgCamera, n, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, 
     return ep, ed, st
 
 
+def sky_uv(exit_dir, status=None):
+    """Equirectangular sky-lookup coordinates of exit directions (the arithmetic of the reference's
+    background_hit, RelativisticRenderEngine.py:366-378): float32 [N,2] = (-phi, 2 theta - 1); NaN where `status`
+    says captured / start-inside / failed.  torch CUDA tensors in -> torch out."""
+    import torch
+
+    d = exit_dir.contiguous()
+    n = d.shape[0]
+    uv = torch.empty((n, 2), dtype=torch.float32, device=d.device)
+    _lib.check(_lib.load().bhg_sky_uv_f32(d.data_ptr(), status.data_ptr() if status is not None else None, n,
+                                          uv.data_ptr(), d.device.index or 0,
+                                          torch.cuda.current_stream(d.device).cuda_stream or None))
+    return uv
+
+
+def trace_camera_sky(cam: BhgCamera, n, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, *, max_step=math.inf,
+                     eps_horizon=0.01, lambda_max=None, mode="parity", refill_threshold=0, device=0, buffers=None):
+    """Camera -> (uv[n,2] float32, status[n]) on the host: generate, trace and map on the device, copy back 12 B/ray."""
+    params = make_params(M, r_sphere, rtol, atol, max_step, eps_horizon, lambda_max, mode, refill_threshold)
+    n = int(n)
+    uv, st = buffers if buffers is not None else (np.empty((n, 2), np.float32), np.empty(n, np.int32))
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    _lib.check(_lib.load().bhg_trace_camera_sky_host(ctypes.byref(cam), p(uv), p(st), n, ctypes.byref(params),
+                                                     int(device)))
+    return uv, st
+
+
 def sum_counters(counters_ptr, status_ptr, n, device=0, stream=0):
     lib = _lib.load()
     a, b, c = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)

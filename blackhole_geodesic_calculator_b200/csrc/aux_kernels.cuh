@@ -88,6 +88,31 @@ __global__ void selftest_kernel(double* out) {
     atomic_max_double(&out[5], e_root5);
 }
 
+// Sky-lookup coordinates of the exit directions: the equirectangular mapping of the
+// reference's background_hit (raytracer/RelativisticRenderEngine.py:366-378,
+// raytracer/LimitedRelativisticRenderEngine.py:383-408):
+//     theta = 1 - acos(d_z)/pi ; phi = atan2(d_y, d_x)/pi ; texture.evaluate((-phi, 2 theta - 1, 0))
+// -> uv = (-phi, 2 theta - 1), computed in FP64 and stored as float2 (texture coordinates).  Captured /
+// failed rays get NaN (the reference paints them black without a lookup, RRE.py:242-244).
+__global__ void sky_uv_kernel(const double* __restrict__ dir, const int32_t* __restrict__ status, long long n,
+                              float2* __restrict__ uv) {
+    const double inv_pi = 0.31830988618379067154;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int st = status ? status[i] : ESCAPED;
+        float2 o;
+        if (st == CAPTURED || st == START_INSIDE_HOLE || st == STEP_FAILED) {
+            o.x = o.y = __int_as_float(0x7fc00000);
+        } else {
+            const double dx = dir[3 * i], dy = dir[3 * i + 1], dz = dir[3 * i + 2];
+            const double theta = 1.0 - acos(dz) * inv_pi;
+            const double phi = atan2(dy, dx) * inv_pi;
+            o.x = (float)(-phi);
+            o.y = (float)(2.0 * theta - 1.0);
+        }
+        uv[i] = o;
+    }
+}
+
 // 16 independent DFMA chains per thread; flops = 2 * 16 * iters per thread
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* sink, int iters, double m) {
     double a[16];

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <mutex>
@@ -47,7 +48,7 @@ struct DeviceCtx {
     std::mutex mu;
     bool ready = false;
     int sm_count = 0;
-    int blocks_per_sm[2][3] = {{0, 0, 0}, {0, 0, 0}};  // [mode][input kind]
+    int blocks_per_sm[2][2] = {{0, 0}, {0, 0}};  // [mode][layout]
     unsigned long long* queue_slots = nullptr;   // kQueueSlots work-queue heads
     std::atomic<unsigned> next_slot{0};
     // staging buffers of the host entry point (grow-only)
@@ -87,12 +88,17 @@ int ensure_device(int device, DeviceCtx** out) {
         int rc;
         if ((rc = query_occupancy<4, bhg::IN_SOA>(&c.blocks_per_sm[0][0]))) return rc;
         if ((rc = query_occupancy<4, bhg::IN_AOS>(&c.blocks_per_sm[0][1]))) return rc;
-        if ((rc = query_occupancy<4, bhg::IN_CAMERA>(&c.blocks_per_sm[0][2]))) return rc;
         if ((rc = query_occupancy<3, bhg::IN_SOA>(&c.blocks_per_sm[1][0]))) return rc;
         if ((rc = query_occupancy<3, bhg::IN_AOS>(&c.blocks_per_sm[1][1]))) return rc;
-        if ((rc = query_occupancy<3, bhg::IN_CAMERA>(&c.blocks_per_sm[1][2]))) return rc;
         BHG_CUDA(cudaMalloc(&c.queue_slots, kQueueSlots * sizeof(unsigned long long)));
         BHG_CUDA(cudaMalloc(&c.totals, 3 * sizeof(long long)));
+        // keep stream-ordered scratch (camera ray buffers) in the pool instead of returning it to the OS at
+        // every synchronisation
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
         c.ready = true;
     }
     *out = &c;
@@ -137,9 +143,9 @@ int convert_camera(const bhg_camera* cam, double r_sphere, bhg::Camera* out) {
     return 0;
 }
 
-// in_kind: bhg::IN_SOA / IN_AOS / IN_CAMERA (cam != nullptr)
+// in_kind: bhg::IN_SOA / IN_AOS
 int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* out, double* out_dir, int32_t* status,
-                 int32_t* counters, const int32_t* order, long long n, int in_kind, const bhg::Camera* cam,
+                 int32_t* counters, const int32_t* order, long long n, int in_kind, int image_width,
                  const bhg_params* p, cudaStream_t stream) {
     if (n == 0) return 0;
     bhg::TraceArgs a;
@@ -154,12 +160,6 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
     a.rtol = p->rtol; a.atol = p->atol; a.max_step = p->max_step;
     a.lambda_max = p->lambda_max > 0.0 ? p->lambda_max : 10.0 * p->r_sphere;
     a.refill_threshold = p->refill_threshold > 0 ? p->refill_threshold : 32;
-    int image_width = p->image_width;
-    if (cam) {
-        a.cam = *cam;
-        // tiles must not straddle the call's first ray: only when the call starts on a 4-row band boundary
-        image_width = (cam->first_ray % (4LL * cam->width) == 0) ? cam->width : 0;
-    }
     a.tile_width = (image_width > 0 && image_width % 8 == 0 && n % (4LL * image_width) == 0 && !order) ? image_width : 0;
     unsigned slot = c.next_slot.fetch_add(1) % kQueueSlots;
     a.queue_head = c.queue_slots + slot;
@@ -169,17 +169,44 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
     long long max_blocks = (long long)c.sm_count * c.blocks_per_sm[mode][in_kind];
     int blocks = (int)(want_blocks < max_blocks ? want_blocks : max_blocks);
     if (mode == BHG_MODE_PARITY) {
-        if (in_kind == bhg::IN_CAMERA) bhg::trace_kernel<4, bhg::IN_CAMERA><<<blocks, 128, 0, stream>>>(a);
-        else if (in_kind == bhg::IN_AOS) bhg::trace_kernel<4, bhg::IN_AOS><<<blocks, 128, 0, stream>>>(a);
+        if (in_kind == bhg::IN_AOS) bhg::trace_kernel<4, bhg::IN_AOS><<<blocks, 128, 0, stream>>>(a);
         else bhg::trace_kernel<4, bhg::IN_SOA><<<blocks, 128, 0, stream>>>(a);
     } else {
-        if (in_kind == bhg::IN_CAMERA) bhg::trace_kernel<3, bhg::IN_CAMERA><<<blocks, 128, 0, stream>>>(a);
-        else if (in_kind == bhg::IN_AOS) bhg::trace_kernel<3, bhg::IN_AOS><<<blocks, 128, 0, stream>>>(a);
+        if (in_kind == bhg::IN_AOS) bhg::trace_kernel<3, bhg::IN_AOS><<<blocks, 128, 0, stream>>>(a);
         else bhg::trace_kernel<3, bhg::IN_SOA><<<blocks, 128, 0, stream>>>(a);
     }
     g_launches.fetch_add(1);
     BHG_CUDA(cudaGetLastError());
     return 0;
+}
+
+// primary rays of `cam` into AoS device buffers (streaming kernel, HBM-bound: 48 B/ray written)
+int launch_generate(DeviceCtx& c, const bhg::Camera& cam, long long n, double* pos, double* dir, int32_t* hit,
+                    cudaStream_t stream) {
+    if (n == 0) return 0;
+    long long blocks = (n + 255) / 256;
+    if (blocks > c.sm_count * 16LL) blocks = c.sm_count * 16LL;
+    bhg::generate_rays_kernel<<<(int)blocks, 256, 0, stream>>>(cam, n, pos, dir, hit);
+    g_launches.fetch_add(1);
+    BHG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// the tile hint of a camera call: valid only when the call starts on a 4-row band boundary
+int camera_image_width(const bhg::Camera& cam) { return (cam.first_ray % (4LL * cam.width) == 0) ? cam.width : 0; }
+
+// rays per pipeline chunk of the host entry points; BHG_CHUNK_RAYS overrides (tuning)
+// (measured on B200, profiles/r1g_chunks.txt: 512 Ki rays is best when rays also travel H2D, 256 Ki when only
+// results travel D2H)
+long long pick_chunk(long long n, long long band, long long big = 1 << 18) {
+    long long chunk = n <= (1 << 16) ? n : (n <= (1 << 20) ? (n + 3) / 4 : big);
+    if (const char* e = getenv("BHG_CHUNK_RAYS")) {
+        long long v = atoll(e);
+        if (v > 0) chunk = v;
+    }
+    if (chunk > n) chunk = n;
+    if (band > 0 && n > chunk) chunk = ((chunk + band - 1) / band) * band;  // whole 4-row bands keep the tile hint
+    return chunk;
 }
 
 int ensure_stage(DeviceCtx* c, size_t need) {
@@ -226,7 +253,8 @@ int bhg_trace_schwarzschild_f64(const double* in, const double* in_dir, double* 
     DeviceCtx* c;
     if ((rc = ensure_device(device, &c))) return rc;
     return launch_trace(*c, in, in_dir, out, out_dir, status, counters, order, n,
-                        layout == BHG_LAYOUT_AOS ? bhg::IN_AOS : bhg::IN_SOA, nullptr, params, (cudaStream_t)stream);
+                        layout == BHG_LAYOUT_AOS ? bhg::IN_AOS : bhg::IN_SOA, params->image_width, params,
+                        (cudaStream_t)stream);
 }
 
 int bhg_trace_schwarzschild_f64_host(const double* entry_pos, const double* entry_dir, double* exit_pos,
@@ -252,11 +280,7 @@ int bhg_trace_schwarzschild_f64_host(const double* entry_pos, const double* entr
     int32_t* d_status = (int32_t*)(base + 4 * vec);
     int32_t* d_cnt = d_status + n;  // 2 n
     // chunked pipeline over 3 streams: H2D(i+1) overlaps trace(i) overlaps D2H(i-1)
-    long long chunk = n <= (1 << 16) ? n : (n <= (1 << 20) ? (n + 3) / 4 : (1 << 18));
-    if (params->image_width > 0 && n > chunk) {  // keep whole 4-row bands in a chunk so the tile hint survives
-        const long long band = 4LL * params->image_width;
-        chunk = ((chunk + band - 1) / band) * band;
-    }
+    const long long chunk = pick_chunk(n, params->image_width > 0 ? 4LL * params->image_width : 0, 1 << 19);
     int si = 0;
     for (long long b = 0; b < n; b += chunk, si = (si + 1) % 3) {
         const long long m = (n - b < chunk) ? (n - b) : chunk;
@@ -267,7 +291,7 @@ int bhg_trace_schwarzschild_f64_host(const double* entry_pos, const double* entr
         // writing attempts/accepted into a 2m block and scattering on the way back
         int32_t* cnt_chunk = counters ? d_cnt + 2 * b : nullptr;
         rc = launch_trace(*c, d_pin + 3 * b, d_din + 3 * b, d_pout + 3 * b, d_dout + 3 * b, d_status + b, cnt_chunk,
-                          nullptr, m, bhg::IN_AOS, nullptr, params, s);
+                          nullptr, m, bhg::IN_AOS, params->image_width, params, s);
         if (rc) return rc;
         BHG_CUDA(cudaMemcpyAsync(exit_pos + 3 * b, d_pout + 3 * b, (size_t)m * 24, cudaMemcpyDeviceToHost, s));
         BHG_CUDA(cudaMemcpyAsync(exit_dir + 3 * b, d_dout + 3 * b, (size_t)m * 24, cudaMemcpyDeviceToHost, s));
@@ -289,13 +313,7 @@ int bhg_generate_rays_f64(const bhg_camera* cam, double r_sphere, int64_t n, dou
     if (n < 0 || (n > 0 && (!pos || !dir))) return fail(BHG_ERR_INVALID_ARGUMENT, "bad n or NULL ray buffer");
     DeviceCtx* c;
     if ((rc = ensure_device(device, &c))) return rc;
-    if (n == 0) return 0;
-    long long blocks = (n + 255) / 256;
-    if (blocks > c->sm_count * 16LL) blocks = c->sm_count * 16LL;
-    bhg::generate_rays_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(dc, n, pos, dir, hit);
-    g_launches.fetch_add(1);
-    BHG_CUDA(cudaGetLastError());
-    return 0;
+    return launch_generate(*c, dc, n, pos, dir, hit, (cudaStream_t)stream);
 }
 
 int bhg_trace_camera_f64(const bhg_camera* cam, double* exit_pos, double* exit_dir, int32_t* status,
@@ -307,8 +325,17 @@ int bhg_trace_camera_f64(const bhg_camera* cam, double* exit_pos, double* exit_d
     if (n > 0 && (!exit_dir || !status)) return fail(BHG_ERR_INVALID_ARGUMENT, "NULL output buffer");
     DeviceCtx* c;
     if ((rc = ensure_device(device, &c))) return rc;
-    return launch_trace(*c, nullptr, nullptr, exit_pos, exit_dir, status, counters, nullptr, n, bhg::IN_CAMERA, &dc,
-                        params, (cudaStream_t)stream);
+    if (n == 0) return 0;
+    // generate (streaming kernel) then trace; the ray buffer is stream-ordered scratch
+    cudaStream_t s = (cudaStream_t)stream;
+    double* rays = nullptr;
+    BHG_CUDA(cudaMallocAsync((void**)&rays, (size_t)n * 48, s));
+    rc = launch_generate(*c, dc, n, rays, rays + 3 * n, nullptr, s);
+    if (!rc)
+        rc = launch_trace(*c, rays, rays + 3 * n, exit_pos, exit_dir, status, counters, nullptr, n, bhg::IN_AOS,
+                          camera_image_width(dc), params, s);
+    cudaFreeAsync(rays, s);
+    return rc;
 }
 
 int bhg_trace_camera_f64_host(const bhg_camera* cam, double* exit_pos, double* exit_dir, int32_t* status,
@@ -323,16 +350,16 @@ int bhg_trace_camera_f64_host(const bhg_camera* cam, double* exit_pos, double* e
     if (n == 0) return 0;
     std::lock_guard<std::mutex> lk(c->host_mu);
     const size_t vec = (size_t)n * 3 * sizeof(double);
-    if ((rc = ensure_stage(c, 2 * vec + (size_t)n * 3 * sizeof(int32_t) + 1024))) return rc;
+    if ((rc = ensure_stage(c, 4 * vec + (size_t)n * 3 * sizeof(int32_t) + 1024))) return rc;
     char* base = (char*)c->stage;
-    double* d_pout = (double*)base;
-    double* d_dout = (double*)(base + vec);
-    int32_t* d_status = (int32_t*)(base + 2 * vec);
+    double* d_pin = (double*)base;
+    double* d_din = (double*)(base + vec);
+    double* d_pout = (double*)(base + 2 * vec);
+    double* d_dout = (double*)(base + 3 * vec);
+    int32_t* d_status = (int32_t*)(base + 4 * vec);
     int32_t* d_cnt = d_status + n;
     // chunks are whole 4-row bands so that every chunk keeps the 8 x 4 tile scheduling
-    const long long band = 4LL * cam->width;
-    long long chunk = n <= (1 << 16) ? n : (n <= (1 << 20) ? (n + 3) / 4 : (1 << 18));
-    if (n > chunk) chunk = ((chunk + band - 1) / band) * band;
+    const long long chunk = pick_chunk(n, 4LL * cam->width);
     int si = 0;
     for (long long b = 0; b < n; b += chunk, si = (si + 1) % 3) {
         const long long m = (n - b < chunk) ? (n - b) : chunk;
@@ -340,8 +367,9 @@ int bhg_trace_camera_f64_host(const bhg_camera* cam, double* exit_pos, double* e
         bhg::Camera cc = dc;
         cc.first_ray = dc.first_ray + b;
         int32_t* cnt_chunk = counters ? d_cnt + 2 * b : nullptr;
-        rc = launch_trace(*c, nullptr, nullptr, exit_pos ? d_pout + 3 * b : nullptr, d_dout + 3 * b, d_status + b,
-                          cnt_chunk, nullptr, m, bhg::IN_CAMERA, &cc, params, s);
+        if ((rc = launch_generate(*c, cc, m, d_pin + 3 * b, d_din + 3 * b, nullptr, s))) return rc;
+        rc = launch_trace(*c, d_pin + 3 * b, d_din + 3 * b, exit_pos ? d_pout + 3 * b : nullptr, d_dout + 3 * b,
+                          d_status + b, cnt_chunk, nullptr, m, bhg::IN_AOS, camera_image_width(cc), params, s);
         if (rc) return rc;
         if (exit_pos) BHG_CUDA(cudaMemcpyAsync(exit_pos + 3 * b, d_pout + 3 * b, (size_t)m * 24, cudaMemcpyDeviceToHost, s));
         BHG_CUDA(cudaMemcpyAsync(exit_dir + 3 * b, d_dout + 3 * b, (size_t)m * 24, cudaMemcpyDeviceToHost, s));
@@ -350,6 +378,62 @@ int bhg_trace_camera_f64_host(const bhg_camera* cam, double* exit_pos, double* e
             BHG_CUDA(cudaMemcpyAsync(counters + b, cnt_chunk, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
             BHG_CUDA(cudaMemcpyAsync(counters + n + b, cnt_chunk + m, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
         }
+    }
+    for (auto& s : c->streams) BHG_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int bhg_sky_uv_f32(const double* exit_dir, const int32_t* status, int64_t n, float* uv, int32_t device, void* stream) {
+    if (n < 0 || (n > 0 && (!exit_dir || !uv))) return fail(BHG_ERR_INVALID_ARGUMENT, "bad n or NULL buffer");
+    DeviceCtx* c;
+    int rc = ensure_device(device, &c);
+    if (rc) return rc;
+    if (n == 0) return 0;
+    long long blocks = (n + 255) / 256;
+    if (blocks > c->sm_count * 16LL) blocks = c->sm_count * 16LL;
+    bhg::sky_uv_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(exit_dir, status, n, (float2*)uv);
+    g_launches.fetch_add(1);
+    BHG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int bhg_trace_camera_sky_host(const bhg_camera* cam, float* uv, int32_t* status, int64_t n, const bhg_params* params,
+                              int32_t device) {
+    int rc = validate(params, n);
+    if (rc) return rc;
+    bhg::Camera dc;
+    if ((rc = convert_camera(cam, params->r_sphere, &dc))) return rc;
+    if (n > 0 && (!uv || !status)) return fail(BHG_ERR_INVALID_ARGUMENT, "NULL output buffer");
+    DeviceCtx* c;
+    if ((rc = ensure_device(device, &c))) return rc;
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(c->host_mu);
+    const size_t vec = (size_t)n * 3 * sizeof(double);
+    if ((rc = ensure_stage(c, 3 * vec + (size_t)n * (8 + 4) + 1024))) return rc;
+    char* base = (char*)c->stage;
+    double* d_pin = (double*)base;
+    double* d_din = (double*)(base + vec);
+    double* d_dout = (double*)(base + 2 * vec);
+    float* d_uv = (float*)(base + 3 * vec);
+    int32_t* d_status = (int32_t*)(base + 3 * vec + (size_t)n * 8);
+    const long long chunk = pick_chunk(n, 4LL * cam->width);
+    int si = 0;
+    for (long long b = 0; b < n; b += chunk, si = (si + 1) % 3) {
+        const long long m = (n - b < chunk) ? (n - b) : chunk;
+        cudaStream_t s = c->streams[si];
+        bhg::Camera cc = dc;
+        cc.first_ray = dc.first_ray + b;
+        if ((rc = launch_generate(*c, cc, m, d_pin + 3 * b, d_din + 3 * b, nullptr, s))) return rc;
+        rc = launch_trace(*c, d_pin + 3 * b, d_din + 3 * b, nullptr, d_dout + 3 * b, d_status + b, nullptr, nullptr, m,
+                          bhg::IN_AOS, camera_image_width(cc), params, s);
+        if (rc) return rc;
+        long long blocks = (m + 255) / 256;
+        if (blocks > c->sm_count * 16LL) blocks = c->sm_count * 16LL;
+        bhg::sky_uv_kernel<<<(int)blocks, 256, 0, s>>>(d_dout + 3 * b, d_status + b, m, (float2*)(d_uv + 2 * b));
+        g_launches.fetch_add(1);
+        BHG_CUDA(cudaGetLastError());
+        BHG_CUDA(cudaMemcpyAsync(uv + 2 * b, d_uv + 2 * b, (size_t)m * 8, cudaMemcpyDeviceToHost, s));
+        BHG_CUDA(cudaMemcpyAsync(status + b, d_status + b, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
     }
     for (auto& s : c->streams) BHG_CUDA(cudaStreamSynchronize(s));
     return 0;

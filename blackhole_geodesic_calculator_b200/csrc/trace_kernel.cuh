@@ -33,12 +33,13 @@ struct TraceArgs {
     int has_outer;
     int refill_threshold;
     int tile_width;  // > 0: queue slots enumerate 8 x 4 pixel tiles of a row-major image of this width
-    Camera cam;      // IN_CAMERA only: rays are generated in the kernel, nothing is read from HBM
 };
 
-// where a ray's entry state comes from
-constexpr int IN_SOA = 0, IN_AOS = 1, IN_CAMERA = 2;
-constexpr int MISSED_SPHERE = 5;  // camera ray that never enters the sphere of influence (IN_CAMERA only)
+// memory layout of the ray buffers
+constexpr int IN_SOA = 0, IN_AOS = 1;
+// A NaN entry position marks a primary ray that never meets the sphere of influence (written by
+// generate_rays_kernel): it is not integrated, keeps its flat direction and gets this status.
+constexpr int MISSED_SPHERE = 5;
 
 // queue slot -> ray index.  With the image hint, 32 consecutive slots (one warp's fetch when it starts empty)
 // cover an 8 x 4 pixel tile, whose rays have far more similar step counts than 32 pixels of one row.
@@ -59,12 +60,10 @@ constexpr int PEND_H = -2;   // horizon event active in the last step
 constexpr int PEND_E = -3;   // outer-sphere event active
 constexpr int PEND_HE = -5;  // both
 
-// returns false only for a camera ray that misses the sphere (k then holds its flat direction)
+// returns false for a ray flagged as missing the sphere (NaN entry position; k holds its flat direction)
 template <int IN>
 __device__ __forceinline__ bool load_ray(const TraceArgs& a, long long idx, double (&x)[3], double (&k)[3]) {
-    if (IN == IN_CAMERA) {
-        return camera_ray(a.cam, idx, x, k);
-    } else if (IN == IN_AOS) {
+    if (IN == IN_AOS) {
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             x[c] = __ldg(a.in + 3 * idx + c);
@@ -77,10 +76,10 @@ __device__ __forceinline__ bool load_ray(const TraceArgs& a, long long idx, doub
             k[c] = __ldg(a.in + (3 + c) * a.n + idx);
         }
     }
-    return true;
+    return x[0] == x[0];  // false iff NaN
 }
 
-// outputs are AoS for IN_AOS / IN_CAMERA (exit positions optional: a.out may be NULL), planes for IN_SOA
+// outputs are AoS for IN_AOS (exit positions optional: a.out may be NULL), planes for IN_SOA
 template <int IN>
 __device__ __forceinline__ void store_ray(const TraceArgs& a, long long idx, const double (&x)[3],
                                           const double (&k)[3], int status, int n_attempt, int n_accept) {

@@ -123,12 +123,16 @@ typedef struct bhg_camera {
 } bhg_camera;
 
 /* Generates n primary rays on the device: pos[n][3] = entry point on the sphere |p| = r_sphere (NaN if the ray
- * misses), dir[n][3] = unit direction, hit[n] (NULL ok) = 0 or BHG_MISSED_SPHERE.  Device buffers. */
+ * misses), dir[n][3] = unit direction, hit[n] (NULL ok) = 0 or BHG_MISSED_SPHERE.  Device buffers.
+ * The trace entry points treat a NaN entry position as "missed": status BHG_MISSED_SPHERE, exit_dir = the
+ * unchanged input direction, exit_pos = NaN. */
 int bhg_generate_rays_f64(const bhg_camera* cam, double r_sphere, int64_t n, double* pos, double* dir, int32_t* hit,
                           int32_t device, void* stream);
 
-/* Fused generate + trace: the whole curved-spacetime part of one frame (or tile) from a 150-byte camera
- * description; no ray buffer is read from memory.  Device output buffers, AoS [n][3]; exit_pos may be NULL when
+/* Generate + trace: the whole curved-spacetime part of one frame (or tile) from a 176-byte camera description;
+ * no ray buffer crosses PCIe.  (A streaming generator kernel writes the rays to stream-ordered device scratch,
+ * then the trace kernel runs: measured faster than generating inside the latency-bound trace kernel.)
+ * Device output buffers, AoS [n][3]; exit_pos may be NULL when
  * the consumer needs directions only (CamEdition.py:228 reads ray_end[...,3:6]; RRE.py:246 uses end_dir only).
  * Rays that miss the sphere get BHG_MISSED_SPHERE.  params->image_width is set from the camera automatically. */
 int bhg_trace_camera_f64(const bhg_camera* cam, double* exit_pos, double* exit_dir, int32_t* status,
@@ -138,6 +142,17 @@ int bhg_trace_camera_f64(const bhg_camera* cam, double* exit_pos, double* exit_d
  * with the integration of the next ones.  exit_pos and counters may be NULL. */
 int bhg_trace_camera_f64_host(const bhg_camera* cam, double* exit_pos, double* exit_dir, int32_t* status,
                               int32_t* counters, int64_t n, const bhg_params* params, int32_t device);
+
+/* Sky-lookup coordinates of exit directions: replaces the arithmetic of background_hit (RRE.py:366-378,
+ * LIM.py:383-408): uv[i] = (-atan2(d_y,d_x)/pi, 2 (1 - acos(d_z)/pi) - 1) as float32 pairs, NaN for rays whose
+ * status is captured / start-inside / failed (the reference paints those black without a lookup); status may
+ * be NULL (all rays mapped).  exit_dir is AoS [n][3].  Device buffers, asynchronous on `stream`. */
+int bhg_sky_uv_f32(const double* exit_dir, const int32_t* status, int64_t n, float* uv, int32_t device, void* stream);
+
+/* Fused camera -> sky coordinates with HOST outputs: generate, trace, map, and copy back only uv[n][2] float32 and
+ * status[n] (12 B/ray instead of 52): everything the host needs to composite a background-only frame. */
+int bhg_trace_camera_sky_host(const bhg_camera* cam, float* uv, int32_t* status, int64_t n, const bhg_params* params,
+                              int32_t device);
 
 /* Pinned host memory for the staging path (optional convenience). */
 void* bhg_host_alloc(int64_t bytes);

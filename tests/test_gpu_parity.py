@@ -263,3 +263,28 @@ def test_fused_camera_trace_equals_generate_then_trace(api):
         band = crit_band(pos.cpu().numpy()[ok], d.cpu().numpy()[ok], 1.0)
         assert_parity(ep[ok], ed[ok], st[ok], o["exit_pos"], o["exit_dir"], o["status"], 60.0, exclude=band)
         assert (cnt[0][ok][~band] == o["n_attempt"][~band]).mean() > 0.999
+
+
+def test_sky_uv_mapping(api):
+    """the equirectangular lookup coordinates of background_hit (RRE.py:366-378)."""
+    import torch
+    from blackhole_geodesic_calculator_b200 import raygen
+    g = load_golden("cfg1_64x64.npz")
+    d = torch.from_numpy(g["exit_dir"]).cuda()
+    st = torch.from_numpy(g["status"].astype(np.int32)).cuda()
+    uv = api.sky_uv(d, st).cpu().numpy()
+    ok = g["status"] == 0
+    theta = 1 - np.arccos(g["exit_dir"][:, 2]) / np.pi          # the reference's expressions, literally
+    phi = np.arctan2(g["exit_dir"][:, 1], g["exit_dir"][:, 0]) / np.pi
+    ref = np.stack([-phi, 2 * theta - 1], axis=1)
+    assert np.abs(uv[ok] - ref[ok]).max() < 1.2e-7            # float32 storage of an FP64 result
+    assert np.isnan(uv[~ok]).all()
+    # fused camera -> uv on the host
+    rot = raygen.look_at_rotation(raygen.CFG_CAMERA_POS)
+    cam = api.make_camera(raygen.CFG_CAMERA_POS, rot, 64, 64, 0.6, 0.6, seed=3, jitter="philox")
+    uv_h, st_h = api.trace_camera_sky(cam, 4096)
+    _, ed, st2 = api.trace_camera(cam, 4096, want_pos=False)
+    assert np.array_equal(st_h, st2)
+    esc = st2 == 0
+    ref = np.stack([-np.arctan2(ed[:, 1], ed[:, 0]) / np.pi, 2 * (1 - np.arccos(ed[:, 2]) / np.pi) - 1], axis=1)
+    assert np.abs(uv_h[esc] - ref[esc]).max() < 1.2e-7 and np.isnan(uv_h[st2 == 1]).all()
