@@ -46,6 +46,11 @@ class BhgCamera(ctypes.Structure):
     ]
 
 
+class BhgExtras(ctypes.Structure):
+    """Mirror of `struct bhg_extras` (include/bhgeo.h)."""
+    _fields_ = [("disk_r_in", ctypes.c_double), ("disk_r_out", ctypes.c_double), ("disk_xy", ctypes.c_void_p)]
+
+
 class BhgError(RuntimeError):
     def __init__(self, code, message):
         super().__init__(f"bhgeo error {code}: {message}")
@@ -60,6 +65,12 @@ _SIGNATURES = {
                                                    ctypes.POINTER(BhgParams), ctypes.c_int32, _P]),
     "bhg_trace_schwarzschild_f64_host": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, ctypes.c_int64,
                                                         ctypes.POINTER(BhgParams), ctypes.c_int32]),
+    "bhg_trace_schwarzschild_f64_ex": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, ctypes.c_int64, ctypes.c_int32,
+                                                      ctypes.POINTER(BhgParams), ctypes.POINTER(BhgExtras),
+                                                      ctypes.c_int32, _P]),
+    "bhg_trace_schwarzschild_f64_host_ex": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, ctypes.c_int64,
+                                                           ctypes.POINTER(BhgParams), ctypes.POINTER(BhgExtras),
+                                                           ctypes.c_int32]),
     "bhg_generate_rays_f64": (ctypes.c_int, [ctypes.POINTER(BhgCamera), ctypes.c_double, ctypes.c_int64, _P, _P, _P,
                                              ctypes.c_int32, _P]),
     "bhg_trace_camera_f64": (ctypes.c_int, [ctypes.POINTER(BhgCamera), _P, _P, _P, _P, ctypes.c_int64,

@@ -92,23 +92,42 @@ class SchwarzschildGeodesic:
         return max(50.0 + 2.0 * 50.0 * (r / 20.0 - 1.0), 10.0 * r)
 
     def ray_trace_batch(self, directions, loc_hits, exit_tolerance=0.2, ratio_obj_to_blackhole=30.0, curve_end=None,
-                        max_step=math.inf, mode="parity"):
+                        max_step=math.inf, mode="parity", disk=None):
         """directions, loc_hits: [N,3] in scene units, relative to the sphere centre.  Returns
-        (end_loc[N,3] scene units, end_dir[N,3] unit, hit_blackhole[N], outside[N], status[N])."""
+        (end_loc[N,3] scene units, end_dir[N,3] unit, hit_blackhole[N], outside[N], status[N]).
+        disk=(R_in, R_out) in r_s units (the engine passes disk_R_in * ratio, disk_R_out * ratio,
+        LimitedRelativisticRenderEngine.py:284-285) appends disk_xy[N,2] in r_s units (NaN = no hit): the
+        `loc` of checkHitDisk (LIM.py:413-438) found in flight."""
         d = np.ascontiguousarray(directions, dtype=np.float64).reshape(-1, 3)
         p = np.ascontiguousarray(loc_hits, dtype=np.float64).reshape(-1, 3)
         ratio = float(ratio_obj_to_blackhole)
         scale = ratio / np.linalg.norm(p, axis=1)          # scene units -> r_s units, per ray
         lam = self.approximateCurveEnd(ratio) if curve_end is None else float(curve_end)
         ms = math.inf if (max_step is None or max_step == -1) else float(max_step)
-        exit_pos, exit_dir, status = api.trace(p * scale[:, None], d, 0.5, ratio, self.rtol, self.atol, max_step=ms,
-                                               eps_horizon=self.eps_horizon, lambda_max=lam, mode=mode,
-                                               device=self.device)
+        res = api.trace(p * scale[:, None], d, 0.5, ratio, self.rtol, self.atol, max_step=ms,
+                        eps_horizon=self.eps_horizon, lambda_max=lam, mode=mode, device=self.device, disk=disk)
+        exit_pos, exit_dir, status = res[:3]
         hit_bh = status == api.CAPTURED
         # 'Outside': the ray did not end on the sphere within exit_tolerance (LIM.py:311-314)
         off = np.abs(np.linalg.norm(exit_pos, axis=1) - ratio) > exit_tolerance
         outside = ~hit_bh & (off | (status != api.ESCAPED))
+        if disk is not None:
+            return exit_pos / scale[:, None], exit_dir, hit_bh, outside, status, res[-1]
         return exit_pos / scale[:, None], exit_dir, hit_bh, outside, status
+
+    @staticmethod
+    def disk_shading_inputs(disk_xy, R_in, R_out, disk_phase=0.0, disk_mean=0.2, disk_stddev=0.3, disk_intensity=1.0):
+        """The per-hit arithmetic of checkHitDisk after the crossing is known (LIM.py:424-436): returns
+        (hit[N], texture_x[N], texture_y[N], intensity[N]); the texture lookup itself stays in Blender."""
+        xd, yd = disk_xy[:, 0], disk_xy[:, 1]
+        hit = np.isfinite(xd)
+        R = np.sqrt(xd * xd + yd * yd)
+        with np.errstate(all="ignore"):
+            scale = (R - R_in) / (R_out - R_in)
+            intensity = disk_intensity * np.exp(-((scale - disk_mean) ** 2) / (2 * disk_stddev**2)) / np.sqrt(
+                2 * np.pi * disk_stddev)
+            texture_x = (disk_phase + np.arccos(xd / R) * (yd / np.abs(yd))) / np.pi
+        return hit, texture_x, scale, intensity
 
     def ray_trace(self, direction, loc_hit, exit_tolerance=0.2, ratio_obj_to_blackhole=30.0, curve_end=None,
                   max_step=math.inf, warnings=False):

@@ -19,7 +19,7 @@ import math
 import numpy as np
 
 from . import _lib
-from ._lib import BhgCamera, BhgParams
+from ._lib import BhgCamera, BhgExtras, BhgParams
 
 ESCAPED, CAPTURED, START_INSIDE_HOLE, LAMBDA_EXHAUSTED, STEP_FAILED, MISSED_SPHERE = 0, 1, 2, 3, 4, 5
 STATUS_NAMES = {0: "ESCAPED", 1: "CAPTURED", 2: "START_INSIDE_HOLE", 3: "LAMBDA_EXHAUSTED", 4: "STEP_FAILED",
@@ -45,20 +45,23 @@ def _is_torch(x):
 
 def trace(entry_pos, entry_dir, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, *, max_step=math.inf,
           eps_horizon=0.01, lambda_max=None, mode="parity", refill_threshold=0, image_width=0, device=0,
-          return_counters=False):
+          return_counters=False, disk=None):
     """Integrate N Schwarzschild null geodesics from sphere entry to exit or capture.
 
     entry_pos, entry_dir : [N,3] float64, BH-centred position and coordinate direction (numpy arrays on the
         host, or torch CUDA tensors, which are processed in place on their device and stream).
     image_width : optional scheduling hint — the rays are a row-major image of this width (the reference's
         s -> y -> x order); warps then integrate 8 x 4 pixel tiles.  Never changes results.
+    disk : optional (r_in, r_out): also return disk_xy[N,2], the first crossing of the equatorial plane z = 0
+        with r_in <= r <= r_out (NaN = none) — the in-flight form of the reference's checkHitDisk
+        (LimitedRelativisticRenderEngine.py:413-438).  Parity mode only.
     Returns (exit_pos[N,3], exit_dir[N,3] unit-norm, status[N] int32) and, with return_counters, an
-    int32 [2,N] array of (RK45 attempts, accepted steps).
+    int32 [2,N] array of (RK45 attempts, accepted steps), then disk_xy if requested.
     """
     params = make_params(M, r_sphere, rtol, atol, max_step, eps_horizon, lambda_max, mode, refill_threshold,
                          image_width)
     if _is_torch(entry_pos):
-        return _trace_torch(entry_pos, entry_dir, params, return_counters)
+        return _trace_torch(entry_pos, entry_dir, params, return_counters, disk)
     lib = _lib.load()
     pos = np.ascontiguousarray(entry_pos, dtype=np.float64)
     dirs = np.ascontiguousarray(entry_dir, dtype=np.float64)
@@ -70,14 +73,21 @@ def trace(entry_pos, entry_dir, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, *, m
     status = np.empty(n, dtype=np.int32)
     counters = np.empty((2, n), dtype=np.int32) if return_counters else None
     p = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
-    _lib.check(lib.bhg_trace_schwarzschild_f64_host(p(pos), p(dirs), p(exit_pos), p(exit_dir), p(status),
-                                                    p(counters), n, ctypes.byref(params), int(device)))
+    disk_xy = np.empty((n, 2), dtype=np.float64) if disk is not None else None
+    extras = BhgExtras(float(disk[0]), float(disk[1]), disk_xy.ctypes.data) if disk is not None else None
+    _lib.check(lib.bhg_trace_schwarzschild_f64_host_ex(p(pos), p(dirs), p(exit_pos), p(exit_dir), p(status),
+                                                       p(counters), n, ctypes.byref(params),
+                                                       ctypes.byref(extras) if extras is not None else None,
+                                                       int(device)))
+    res = (exit_pos, exit_dir, status)
     if return_counters:
-        return exit_pos, exit_dir, status, counters
-    return exit_pos, exit_dir, status
+        res += (counters,)
+    if disk is not None:
+        res += (disk_xy,)
+    return res
 
 
-def _trace_torch(entry_pos, entry_dir, params, return_counters):
+def _trace_torch(entry_pos, entry_dir, params, return_counters, disk=None):
     import torch
 
     if not (entry_pos.is_cuda and entry_dir.is_cuda):
@@ -92,21 +102,32 @@ def _trace_torch(entry_pos, entry_dir, params, return_counters):
     exit_dir = torch.empty_like(pos)
     status = torch.empty(n, dtype=torch.int32, device=dev)
     counters = torch.empty((2, n), dtype=torch.int32, device=dev) if return_counters else None
+    disk_xy = torch.empty((n, 2), dtype=torch.float64, device=dev) if disk is not None else None
+    extras = BhgExtras(float(disk[0]), float(disk[1]), disk_xy.data_ptr()) if disk is not None else None
     trace_device(pos.data_ptr(), dirs.data_ptr(), exit_pos.data_ptr(), exit_dir.data_ptr(), status.data_ptr(),
                  counters.data_ptr() if counters is not None else None, None, n, LAYOUT_AOS, params,
-                 dev.index or 0, torch.cuda.current_stream(dev).cuda_stream)
+                 dev.index or 0, torch.cuda.current_stream(dev).cuda_stream, extras)
+    res = (exit_pos, exit_dir, status)
     if return_counters:
-        return exit_pos, exit_dir, status, counters
-    return exit_pos, exit_dir, status
+        res += (counters,)
+    if disk is not None:
+        res += (disk_xy,)
+    return res
 
 
 def trace_device(in_ptr, in_dir_ptr, out_ptr, out_dir_ptr, status_ptr, counters_ptr, order_ptr, n, layout,
-                 params: BhgParams, device=0, stream=0):
+                 params: BhgParams, device=0, stream=0, extras: BhgExtras = None):
     """Raw device-pointer call (asynchronous on `stream`); the benchmark's hot call."""
     lib = _lib.load()
-    _lib.check(lib.bhg_trace_schwarzschild_f64(in_ptr, in_dir_ptr, out_ptr, out_dir_ptr, status_ptr, counters_ptr,
-                                               order_ptr, int(n), int(layout), ctypes.byref(params), int(device),
-                                               stream or None))
+    if extras is None:
+        _lib.check(lib.bhg_trace_schwarzschild_f64(in_ptr, in_dir_ptr, out_ptr, out_dir_ptr, status_ptr,
+                                                   counters_ptr, order_ptr, int(n), int(layout),
+                                                   ctypes.byref(params), int(device), stream or None))
+    else:
+        _lib.check(lib.bhg_trace_schwarzschild_f64_ex(in_ptr, in_dir_ptr, out_ptr, out_dir_ptr, status_ptr,
+                                                      counters_ptr, order_ptr, int(n), int(layout),
+                                                      ctypes.byref(params), ctypes.byref(extras), int(device),
+                                                      stream or None))
 
 
 def make_camera(origin, rotation, width, height, fov_x=0.6, fov_y=0.6, seed=42, jitter="philox", first_ray=0):

@@ -146,8 +146,13 @@ int convert_camera(const bhg_camera* cam, double r_sphere, bhg::Camera* out) {
 // in_kind: bhg::IN_SOA / IN_AOS
 int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* out, double* out_dir, int32_t* status,
                  int32_t* counters, const int32_t* order, long long n, int in_kind, int image_width,
-                 const bhg_params* p, cudaStream_t stream) {
+                 const bhg_params* p, cudaStream_t stream, const bhg_extras* ex = nullptr) {
     if (n == 0) return 0;
+    const bool disk = ex && ex->disk_xy && ex->disk_r_out > 0.0;
+    if (disk && p->mode != BHG_MODE_PARITY)
+        return fail(BHG_ERR_INVALID_ARGUMENT, "the disk-crossing event is available in parity mode only");
+    if (disk && in_kind != bhg::IN_AOS)
+        return fail(BHG_ERR_INVALID_ARGUMENT, "the disk-crossing event needs the AOS layout");
     bhg::TraceArgs a;
     memset(&a, 0, sizeof(a));
     a.in = in; a.in_dir = in_dir; a.out = out; a.out_dir = out_dir;
@@ -161,6 +166,7 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
     a.lambda_max = p->lambda_max > 0.0 ? p->lambda_max : 10.0 * p->r_sphere;
     a.refill_threshold = p->refill_threshold > 0 ? p->refill_threshold : 32;
     a.tile_width = (image_width > 0 && image_width % 8 == 0 && n % (4LL * image_width) == 0 && !order) ? image_width : 0;
+    if (disk) { a.disk_r_in = ex->disk_r_in; a.disk_r_out = ex->disk_r_out; a.disk_xy = ex->disk_xy; }
     unsigned slot = c.next_slot.fetch_add(1) % kQueueSlots;
     a.queue_head = c.queue_slots + slot;
     BHG_CUDA(cudaMemsetAsync(a.queue_head, 0, sizeof(unsigned long long), stream));
@@ -168,7 +174,9 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
     long long want_blocks = (n + 127) / 128;
     long long max_blocks = (long long)c.sm_count * c.blocks_per_sm[mode][in_kind];
     int blocks = (int)(want_blocks < max_blocks ? want_blocks : max_blocks);
-    if (mode == BHG_MODE_PARITY) {
+    if (disk) {
+        bhg::trace_kernel<4, bhg::IN_AOS, true><<<blocks, 128, 0, stream>>>(a);
+    } else if (mode == BHG_MODE_PARITY) {
         if (in_kind == bhg::IN_AOS) bhg::trace_kernel<4, bhg::IN_AOS><<<blocks, 128, 0, stream>>>(a);
         else bhg::trace_kernel<4, bhg::IN_SOA><<<blocks, 128, 0, stream>>>(a);
     } else {
@@ -244,6 +252,14 @@ void bhg_default_params(bhg_params* p) {
 int bhg_trace_schwarzschild_f64(const double* in, const double* in_dir, double* out, double* out_dir,
                                 int32_t* status, int32_t* counters, const int32_t* order, int64_t n,
                                 int32_t layout, const bhg_params* params, int32_t device, void* stream) {
+    return bhg_trace_schwarzschild_f64_ex(in, in_dir, out, out_dir, status, counters, order, n, layout, params, nullptr,
+                                          device, stream);
+}
+
+int bhg_trace_schwarzschild_f64_ex(const double* in, const double* in_dir, double* out, double* out_dir,
+                                   int32_t* status, int32_t* counters, const int32_t* order, int64_t n,
+                                   int32_t layout, const bhg_params* params, const bhg_extras* extras,
+                                   int32_t device, void* stream) {
     int rc = validate(params, n);
     if (rc) return rc;
     if (layout != BHG_LAYOUT_SOA && layout != BHG_LAYOUT_AOS) return fail(BHG_ERR_INVALID_ARGUMENT, "unknown layout %d", layout);
@@ -254,12 +270,19 @@ int bhg_trace_schwarzschild_f64(const double* in, const double* in_dir, double* 
     if ((rc = ensure_device(device, &c))) return rc;
     return launch_trace(*c, in, in_dir, out, out_dir, status, counters, order, n,
                         layout == BHG_LAYOUT_AOS ? bhg::IN_AOS : bhg::IN_SOA, params->image_width, params,
-                        (cudaStream_t)stream);
+                        (cudaStream_t)stream, extras);
 }
 
 int bhg_trace_schwarzschild_f64_host(const double* entry_pos, const double* entry_dir, double* exit_pos,
                                      double* exit_dir, int32_t* status, int32_t* counters, int64_t n,
                                      const bhg_params* params, int32_t device) {
+    return bhg_trace_schwarzschild_f64_host_ex(entry_pos, entry_dir, exit_pos, exit_dir, status, counters, n, params,
+                                               nullptr, device);
+}
+
+int bhg_trace_schwarzschild_f64_host_ex(const double* entry_pos, const double* entry_dir, double* exit_pos,
+                                        double* exit_dir, int32_t* status, int32_t* counters, int64_t n,
+                                        const bhg_params* params, const bhg_extras* extras, int32_t device) {
     int rc = validate(params, n);
     if (rc) return rc;
     if (n > 0 && (!entry_pos || !entry_dir || !exit_pos || !exit_dir || !status))
@@ -270,9 +293,11 @@ int bhg_trace_schwarzschild_f64_host(const double* entry_pos, const double* entr
     std::lock_guard<std::mutex> lk(c->host_mu);
     // device staging: pos_in | dir_in | pos_out | dir_out | status | counters
     const size_t vec = (size_t)n * 3 * sizeof(double);
-    const size_t need = 4 * vec + (size_t)n * 3 * sizeof(int32_t) + 1024;
+    const bool disk = extras && extras->disk_xy && extras->disk_r_out > 0.0;
+    const size_t need = 4 * vec + (size_t)n * 3 * sizeof(int32_t) + (disk ? (size_t)n * 16 : 0) + 1024;
     if ((rc = ensure_stage(c, need))) return rc;
     char* base = (char*)c->stage;
+    double* d_disk = (double*)(base + 4 * vec + (((size_t)n * 3 * sizeof(int32_t) + 15) / 16) * 16);
     double* d_pin = (double*)base;
     double* d_din = (double*)(base + vec);
     double* d_pout = (double*)(base + 2 * vec);
@@ -290,9 +315,12 @@ int bhg_trace_schwarzschild_f64_host(const double* entry_pos, const double* entr
         // counters of a chunk live at [b, b+m) and [n + b, ...): give the kernel a chunk-local view by
         // writing attempts/accepted into a 2m block and scattering on the way back
         int32_t* cnt_chunk = counters ? d_cnt + 2 * b : nullptr;
+        bhg_extras ex_chunk;
+        if (disk) { ex_chunk = *extras; ex_chunk.disk_xy = d_disk + 2 * b; }
         rc = launch_trace(*c, d_pin + 3 * b, d_din + 3 * b, d_pout + 3 * b, d_dout + 3 * b, d_status + b, cnt_chunk,
-                          nullptr, m, bhg::IN_AOS, params->image_width, params, s);
+                          nullptr, m, bhg::IN_AOS, params->image_width, params, s, disk ? &ex_chunk : nullptr);
         if (rc) return rc;
+        if (disk) BHG_CUDA(cudaMemcpyAsync(extras->disk_xy + 2 * b, d_disk + 2 * b, (size_t)m * 16, cudaMemcpyDeviceToHost, s));
         BHG_CUDA(cudaMemcpyAsync(exit_pos + 3 * b, d_pout + 3 * b, (size_t)m * 24, cudaMemcpyDeviceToHost, s));
         BHG_CUDA(cudaMemcpyAsync(exit_dir + 3 * b, d_dout + 3 * b, (size_t)m * 24, cudaMemcpyDeviceToHost, s));
         BHG_CUDA(cudaMemcpyAsync(status + b, d_status + b, (size_t)m * 4, cudaMemcpyDeviceToHost, s));

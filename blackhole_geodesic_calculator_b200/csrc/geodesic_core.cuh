@@ -452,15 +452,16 @@ __device__ __forceinline__ double dense_eval(const double (&q)[4], double yold, 
 // Root of r(s) - target on s in [0,1] given a sign change between the end points.
 // scipy uses brentq(xtol=rtol=4 eps) on the same quartic (ivp.py:52-77); any bracketing method that
 // converges to the last bit of s lands inside brentq's own tolerance.  Newton with bisection safeguard.
-__device__ __forceinline__ double event_root(const double (&q)[4], double rold, double h, double target) {
-    double lo = 0.0, hi = 1.0;
+__device__ __forceinline__ double event_root(const double (&q)[4], double rold, double h, double target,
+                                             double s_hi = 1.0) {
+    double lo = 0.0, hi = s_hi;
     double flo = rold - target;
-    double fhi = dense_eval(q, rold, h, 1.0) - target;
+    double fhi = dense_eval(q, rold, h, s_hi) - target;
     if (flo == 0.0) return 0.0;
-    if (fhi == 0.0) return 1.0;
+    if (fhi == 0.0) return s_hi;
     const bool lo_neg = flo < 0.0;
-    double s = flo / (flo - fhi);  // secant start
-    if (!(s > 0.0 && s < 1.0)) s = 0.5;
+    double s = s_hi * (flo / (flo - fhi));  // secant start
+    if (!(s > 0.0 && s < s_hi)) s = 0.5 * s_hi;
     for (int it = 0; it < 80; it++) {
         const double fs = dense_eval(q, rold, h, s) - target;
         if (fs == 0.0) return s;

@@ -33,6 +33,9 @@ struct TraceArgs {
     int has_outer;
     int refill_threshold;
     int tile_width;  // > 0: queue slots enumerate 8 x 4 pixel tiles of a row-major image of this width
+    // DISK variant only: first crossing of the equatorial plane with disk_r_in <= r <= disk_r_out
+    double disk_r_in, disk_r_out;
+    double* disk_xy;  // [n][2], NaN = no hit
 };
 
 // memory layout of the ray buffers
@@ -214,12 +217,43 @@ __device__ __forceinline__ bool all_finite(const double (&k)[NK], const double (
     return ok;
 }
 
+// Equatorial-plane crossing inside the step [0, s_max] of the dense output (non-terminal event):
+// the continuous form of the reference's checkHitDisk polyline scan (LimitedRelativisticRenderEngine.py:413-438:
+// z sign change -> crossing point -> R_in <= R <= R_out).  z = r cos(theta) changes sign where theta crosses
+// pi/2 + m pi; the crossing is located on the quartic interpolant of theta exactly like the terminal events.
+// Returns true (and writes the in-plane hit point) for a crossing inside the annulus.
+__device__ __forceinline__ bool disk_crossing(const TraceArgs& a, long long idx, const double (&k)[4],
+                                              const double (&x)[4], const double (&K)[7][4], double h, double s_max) {
+    const double half_pi = 1.57079632679489661923, inv_pi = 0.31830988618379067154, pi = 3.14159265358979323846;
+    double q[4];
+    dense_coeffs_x(k[2], K[0][2], K[1][2], K[2][2], K[3][2], K[4][2], K[5][2], h, q);
+    const double th_end = dense_eval(q, x[2], h, s_max);
+    const double m0 = floor((x[2] - half_pi) * inv_pi), m1 = floor((th_end - half_pi) * inv_pi);
+    if (m0 == m1) return false;
+    const double m = m1 > m0 ? m0 + 1.0 : m0;  // first cell boundary in the direction of motion
+    const double target = fma(m, pi, half_pi);
+    const double s = event_root(q, x[2], h, target, s_max);
+    double qr[4], qp[4];
+    dense_coeffs_x(k[1], K[0][1], K[1][1], K[2][1], K[3][1], K[4][1], K[5][1], h, qr);
+    const double r = dense_eval(qr, x[1], h, s);
+    if (!(r >= a.disk_r_in && r <= a.disk_r_out)) return false;
+    dense_coeffs_x(k[3], K[0][3], K[1][3], K[2][3], K[3][3], K[4][3], K[5][3], h, qp);
+    const double ph = dense_eval(qp, x[3], h, s);
+    double sp, cp;
+    sincos_tab(ph, &sp, &cp);
+    const double st = (((long long)m) & 1) ? -1.0 : 1.0;  // sin(pi/2 + m pi)
+    a.disk_xy[2 * idx] = r * st * cp;
+    a.disk_xy[2 * idx + 1] = r * st * sp;
+    return true;
+}
+
 #ifndef BHG_MIN_BLOCKS
 #define BHG_MIN_BLOCKS 4
 #endif
 
-template <int NK, int IN>
+template <int NK, int IN, bool DISK = false>
 __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceArgs a) {
+    static_assert(!DISK || NK == 4, "the disk event is defined for the spherical (parity) state");
     constexpr int IR = 1;  // index of r in x
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -231,6 +265,7 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
     int state = LANE_EMPTY;
     int n_attempt = 0, n_accept = 0;
     bool rejected = false;
+    bool disk_hit = false;
     bool exhausted = false;  // warp-uniform: queue has no more rays
     const int T = a.refill_threshold;
     const double t_bound = a.lambda_max;
@@ -268,6 +303,9 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
                     if (state == PEND_E || state == PEND_HE) s_e = event_root(q, x[IR], h, a.r_sphere);
                     const double s = fmin(s_h, s_e);  // earliest terminal event (ivp.py:117-126)
                     final_status = (s_h <= s_e) ? CAPTURED : ESCAPED;
+                    if constexpr (DISK) {  // crossings before the terminal root still count
+                        if (!disk_hit) disk_hit = disk_crossing(a, idx, k, x, K, h, s);
+                    }
 #pragma unroll
                     for (int i = 0; i < NK; i++) {
                         double qk[4], qx[4];
@@ -294,6 +332,9 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
                     exit_state<NK>(k, x, x0, k0, xo, ko);
                 }
                 store_ray<IN>(a, idx, xo, ko, final_status, n_attempt, n_accept);
+                if constexpr (DISK) {
+                    if (!disk_hit) a.disk_xy[2 * idx] = a.disk_xy[2 * idx + 1] = __longlong_as_double(0x7ff8000000000000LL);
+                }
                 state = LANE_EMPTY;
             }
             // ---------------- refill idle lanes ----------------
@@ -313,6 +354,7 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
                         n_attempt = 0;
                         n_accept = 0;
                         rejected = false;
+                        disk_hit = false;
                         t = 0.0;
                         if (!enters) {
                             state = MISSED_SPHERE;
@@ -360,6 +402,13 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
                         state = act_h ? (act_e ? PEND_HE : PEND_H) : PEND_E;
                         h_abs = h;  // keep the step length for the dense output
                     } else {
+                        if constexpr (DISK) {  // non-terminal plane-crossing event on this accepted step
+                            if (!disk_hit) {
+                                const double half_pi = 1.57079632679489661923, inv_pi = 0.31830988618379067154;
+                                if (floor((x[2] - half_pi) * inv_pi) != floor((xn[2] - half_pi) * inv_pi))
+                                    disk_hit = disk_crossing(a, idx, k, x, K, h, 1.0);
+                            }
+                        }
                         h_abs *= factor;
                         t = t_new;
                         rejected = false;

@@ -98,6 +98,25 @@ int bhg_trace_schwarzschild_f64(const double* in, const double* in_dir, double* 
                                 int32_t* status, int32_t* counters, const int32_t* order, int64_t n,
                                 int32_t layout, const bhg_params* params, int32_t device, void* stream);
 
+/* Optional in-flight products of the same integration.  disk_xy (n x 2 doubles, NaN = no
+ * hit) receives the first crossing of the equatorial plane z = 0 whose radius lies in [disk_r_in, disk_r_out]:
+ * the continuous form of checkHitDisk's polyline scan (LimitedRelativisticRenderEngine.py:283-302,413-438),
+ * located on the dense output like the terminal events; crossings after capture / exit do not count.
+ * Parity mode only.  Never changes exit_pos / exit_dir / status. */
+typedef struct bhg_extras {
+    double disk_r_in, disk_r_out; /* same length unit as M; the disk is off unless disk_r_out > 0 and disk_xy != NULL */
+    double* disk_xy;
+} bhg_extras;
+
+/* bhg_trace_schwarzschild_f64 / _host with extras (extras == NULL is identical to the plain call). */
+int bhg_trace_schwarzschild_f64_ex(const double* in, const double* in_dir, double* out, double* out_dir,
+                                   int32_t* status, int32_t* counters, const int32_t* order, int64_t n,
+                                   int32_t layout, const bhg_params* params, const bhg_extras* extras,
+                                   int32_t device, void* stream);
+int bhg_trace_schwarzschild_f64_host_ex(const double* entry_pos, const double* entry_dir, double* exit_pos,
+                                        double* exit_dir, int32_t* status, int32_t* counters, int64_t n,
+                                        const bhg_params* params, const bhg_extras* extras, int32_t device);
+
 /* Same, on HOST [N,3] arrays (numpy, Blender's bundled Python): stages H2D, traces, stages D2H, and returns
  * when the results are in the host buffers.  Pinned buffers (bhg_host_alloc) are copied asynchronously in
  * overlapping chunks.  counters may be NULL. */

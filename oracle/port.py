@@ -31,7 +31,7 @@ def lib():
         D = ctypes.c_double
         P = ctypes.c_void_p
         _lib.bhg_oracle_trace.argtypes = [P, P, ctypes.c_int64, D, D, D, D, D, D, D, ctypes.c_int, ctypes.c_int,
-                                          P, P, P, P, P, P, P]
+                                          P, P, P, P, P, P, P, D, D, P]
         _lib.bhg_oracle_trace.restype = ctypes.c_int
         _lib.bhg_oracle_max_threads.restype = ctypes.c_int
     return _lib
@@ -42,8 +42,8 @@ def max_threads():
 
 
 def trace(entry_pos, entry_dir, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, max_step=np.inf, eps_horizon=0.01,
-          lambda_max=None, mode=0, nthreads=0):
-    """Returns dict(exit_pos, exit_dir, status, nfev, n_accept, n_attempt, lam)."""
+          lambda_max=None, mode=0, nthreads=0, disk=None):
+    """Returns dict(exit_pos, exit_dir, status, nfev, n_accept, n_attempt, lam[, disk_xy])."""
     pos = np.ascontiguousarray(entry_pos, dtype=np.float64).reshape(-1, 3)
     dirs = np.ascontiguousarray(entry_dir, dtype=np.float64).reshape(-1, 3)
     n = pos.shape[0]
@@ -52,9 +52,13 @@ def trace(entry_pos, entry_dir, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, max_
     out = dict(exit_pos=np.empty((n, 3)), exit_dir=np.empty((n, 3)), status=np.empty(n, np.int32),
                nfev=np.empty(n, np.int32), n_accept=np.empty(n, np.int32), n_attempt=np.empty(n, np.int32),
                lam=np.empty(n))
+    if disk is not None:
+        out["disk_xy"] = np.empty((n, 2))
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     rc = lib().bhg_oracle_trace(p(pos), p(dirs), n, M, r_sphere, rtol, atol, max_step, eps_horizon, lambda_max,
                                 int(mode), int(nthreads), p(out["exit_pos"]), p(out["exit_dir"]), p(out["status"]),
-                                p(out["nfev"]), p(out["n_accept"]), p(out["n_attempt"]), p(out["lam"]))
+                                p(out["nfev"]), p(out["n_accept"]), p(out["n_attempt"]), p(out["lam"]),
+                                float(disk[0]) if disk is not None else 0.0, float(disk[1]) if disk is not None else 0.0,
+                                p(out["disk_xy"]) if disk is not None else None)
     assert rc == 0
     return out

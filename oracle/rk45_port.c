@@ -136,13 +136,15 @@ static double select_initial_step(const sys_t* S, double t0, const double* y0, d
 }
 
 /* r-component of the dense output minus target, at absolute time t (rk.py:715-738) */
-typedef struct { double t_old, h, r_old, q[4], target; } dense_r_t;
+typedef struct { double t_old, h, r_old, q[4], target; int use_cos; } dense_r_t;
 
 static double dense_r(const dense_r_t* D, double t) {
     double x = (t - D->t_old) / D->h;
     double p1 = x, p2 = p1 * x, p3 = p2 * x, p4 = p3 * x; /* np.cumprod */
     double acc = D->q[0] * p1 + D->q[1] * p2 + D->q[2] * p3 + D->q[3] * p4;
-    return (D->h * acc + D->r_old) - D->target;
+    double v = D->h * acc + D->r_old;
+    if (D->use_cos) return cos(v);   /* plane-crossing event g = cos(theta) */
+    return v - D->target;
 }
 
 /* Brent's method as scipy/optimize/Zeros/brentq.c (xtol, rtol, maxiter=100) */
@@ -192,7 +194,11 @@ typedef struct {
     double y[NMAX];  /* state at termination (event root, t_bound, or last good state) */
     double lam;
     int status, nfev, n_accept, n_attempt;
+    double disk_xy[2]; /* first equatorial-plane crossing inside [disk_in, disk_out], else NaN */
 } ray_out_t;
+
+/* disk annulus for the non-terminal plane-crossing event (parity mode only); r_out <= 0 disables */
+typedef struct { double r_in, r_out; } disk_t;
 
 static int all_finite(const double* y, int n) {
     for (int i = 0; i < n; i++) if (!isfinite(y[i])) return 0;
@@ -200,8 +206,20 @@ static int all_finite(const double* y, int n) {
 }
 
 /* solve_ivp(fun, (0, lambda_max), y0, RK45, events=[hit_blackhole(dir 0), reached_end(dir +1)]) */
+static void dense_all(const sys_t* S, double K[7][NMAX], const double* y_old, double h, double x, double* y) {
+    double p1 = x, p2 = p1 * x, p3 = p2 * x, p4 = p3 * x;
+    for (int i = 0; i < S->n; i++) {
+        double q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+        for (int j = 0; j < 7; j++) {
+            q0 += K[j][i] * P_[j][0]; q1 += K[j][i] * P_[j][1];
+            q2 += K[j][i] * P_[j][2]; q3 += K[j][i] * P_[j][3];
+        }
+        y[i] = h * (q0 * p1 + q1 * p2 + q2 * p3 + q3 * p4) + y_old[i];
+    }
+}
+
 static void integrate(const sys_t* S, const double* y0, double r_horizon_ev, double r_sphere, double rtol, double atol,
-                      double max_step, double t_bound, ray_out_t* out) {
+                      double max_step, double t_bound, const disk_t* disk, ray_out_t* out) {
     const int n = S->n, ir = S->ir;
     double t = 0.0, y[NMAX], f[NMAX], K[7][NMAX], y_new[NMAX], ytmp[NMAX];
     int nfev = 0, n_accept = 0, n_attempt = 0;
@@ -211,6 +229,10 @@ static void integrate(const sys_t* S, const double* y0, double r_horizon_ev, dou
     const double err_exp = -1.0 / 5;                                  /* rk.py:102 */
     const int have_outer = isfinite(r_sphere);
     double g_h = y[ir] - r_horizon_ev, g_e = have_outer ? y[ir] - r_sphere : -1.0; /* ivp.py:653 */
+    const int have_disk = disk && disk->r_out > 0 && n == 8;
+    double g_d = have_disk ? cos(y[5]) : 1.0;
+    out->disk_xy[0] = out->disk_xy[1] = NAN;
+    int disk_hit = 0;
     int status = -2;
     while (status == -2) {
         /* ---- OdeSolver.step (base.py:179-210) ---- */
@@ -284,9 +306,22 @@ static void integrate(const sys_t* S, const double* y0, double r_horizon_ev, dou
         double g_h_new = y[ir] - r_horizon_ev, g_e_new = have_outer ? y[ir] - r_sphere : -1.0;
         int act_h = ((g_h <= 0 && g_h_new >= 0) || (g_h >= 0 && g_h_new <= 0)); /* direction 0 */
         int act_e = have_outer && (g_e <= 0 && g_e_new >= 0);                   /* direction +1 */
+        double g_d_new = have_disk ? cos(y[5]) : 1.0;
+        int act_d = have_disk && !disk_hit && ((g_d <= 0 && g_d_new >= 0) || (g_d >= 0 && g_d_new <= 0));
+        double root_d = INFINITY;
+        if (act_d) { /* non-terminal: root of cos(theta(t)) on the dense output */
+            dense_r_t D;
+            D.t_old = t_old; D.h = t - t_old; D.r_old = y_old[5]; D.target = 0; D.use_cos = 1;
+            for (int c = 0; c < 4; c++) {
+                double q = 0;
+                for (int j = 0; j < 7; j++) q += K[j][5] * P_[j][c];
+                D.q[c] = q;
+            }
+            root_d = brentq(&D, t_old, t, 4 * DBL_EPSILON, 4 * DBL_EPSILON);
+        }
         if (act_h || act_e) {
             dense_r_t D;
-            D.t_old = t_old; D.h = t - t_old; D.r_old = y_old_r;
+            D.t_old = t_old; D.h = t - t_old; D.r_old = y_old_r; D.use_cos = 0;
             for (int c = 0; c < 4; c++) {
                 double q = 0;
                 for (int j = 0; j < 7; j++) q += K[j][ir] * P_[j][c];
@@ -297,6 +332,15 @@ static void integrate(const sys_t* S, const double* y0, double r_horizon_ev, dou
             if (act_e) { D.target = r_sphere; root_e = brentq(&D, t_old, t, 4 * DBL_EPSILON, 4 * DBL_EPSILON); }
             double root = root_h <= root_e ? root_h : root_e;   /* earliest terminal root (ivp.py:117-126) */
             status = root_h <= root_e ? CAPTURED : ESCAPED;
+            if (act_d && root_d <= root) { /* events before the terminal one still count (ivp.py:117-126) */
+                double yc[NMAX];
+                dense_all(S, K, y_old, t - t_old, (root_d - t_old) / (t - t_old), yc);
+                if (yc[3] >= disk->r_in && yc[3] <= disk->r_out) {
+                    double st = sin(yc[5]);
+                    out->disk_xy[0] = yc[3] * st * cos(yc[7]); out->disk_xy[1] = yc[3] * st * sin(yc[7]);
+                    disk_hit = 1;
+                }
+            }
             /* y = sol(root) */
             double x = (root - t_old) / (t - t_old);
             double p1 = x, p2 = p1 * x, p3 = p2 * x, p4 = p3 * x;
@@ -311,7 +355,16 @@ static void integrate(const sys_t* S, const double* y0, double r_horizon_ev, dou
             t = root;
             break;
         }
-        g_h = g_h_new; g_e = g_e_new;
+        if (act_d) {
+            double yc[NMAX];
+            dense_all(S, K, y_old, t - t_old, (root_d - t_old) / (t - t_old), yc);
+            if (yc[3] >= disk->r_in && yc[3] <= disk->r_out) {
+                double st = sin(yc[5]);
+                out->disk_xy[0] = yc[3] * st * cos(yc[7]); out->disk_xy[1] = yc[3] * st * sin(yc[7]);
+                disk_hit = 1;
+            }
+        }
+        g_h = g_h_new; g_e = g_e_new; g_d = g_d_new;
         if (finished) { status = LAMBDA_EXHAUSTED; break; }
     }
     if (!all_finite(y, n)) status = STEP_FAILED;
@@ -320,11 +373,13 @@ static void integrate(const sys_t* S, const double* y0, double r_horizon_ev, dou
 }
 
 static void trace_parity(const double* X, const double* Kc, double M, double r_sphere, double rtol, double atol,
-                         double max_step, double eps, double lambda_max, double* xo, double* ko, ray_out_t* o) {
+                         double max_step, double eps, double lambda_max, const disk_t* disk, double* xo, double* ko,
+                         ray_out_t* o) {
     double rs = 2 * M;
     double x = X[0], yv = X[1], z = X[2], kx = Kc[0], ky = Kc[1], kz = Kc[2];
     double rho2 = x * x + yv * yv, r2 = rho2 + z * z, r = sqrt(r2), rho = sqrt(rho2);
     o->status = START_INSIDE_HOLE; o->nfev = 0; o->n_accept = 0; o->n_attempt = 0; o->lam = 0;
+    o->disk_xy[0] = o->disk_xy[1] = NAN;
     for (int i = 0; i < 3; i++) { xo[i] = NAN; ko[i] = NAN; }
     if (!(r > rs + eps)) return;
     double th = acos(z / r), ph = atan2(yv, x);
@@ -337,7 +392,7 @@ static void trace_parity(const double* X, const double* Kc, double M, double r_s
     double y0[8] = {k_t, 0.0, k_r, r, k_th, th, k_ph, ph};
     if (!all_finite(y0, 8)) { o->status = STEP_FAILED; return; } /* scipy base.py:21 refuses such a y0 */
     sys_t S = {8, 3, rs};
-    integrate(&S, y0, rs + eps, r_sphere, rtol, atol, max_step, lambda_max, o);
+    integrate(&S, y0, rs + eps, r_sphere, rtol, atol, max_step, lambda_max, disk, o);
     const double* y = o->y;
     double st = sin(y[5]), ct = cos(y[5]), sp = sin(y[7]), cp = cos(y[7]);
     double R = y[3];
@@ -355,6 +410,7 @@ static void trace_plane(const double* X, const double* Kc, double M, double r_sp
     double rs = 2 * M;
     double r = sqrt(X[0] * X[0] + X[1] * X[1] + X[2] * X[2]);
     o->status = START_INSIDE_HOLE; o->nfev = 0; o->n_accept = 0; o->n_attempt = 0; o->lam = 0;
+    o->disk_xy[0] = o->disk_xy[1] = NAN;
     for (int i = 0; i < 3; i++) { xo[i] = NAN; ko[i] = NAN; }
     if (!(r > rs + eps)) return;
     double e1[3] = {X[0] / r, X[1] / r, X[2] / r};
@@ -369,7 +425,7 @@ static void trace_plane(const double* X, const double* Kc, double M, double r_sp
     double y0[6] = {k_t, 0.0, k_r, r, k_ph, 0.0};
     if (!all_finite(y0, 6)) { o->status = STEP_FAILED; return; }
     sys_t S = {6, 3, rs};
-    integrate(&S, y0, rs + eps, r_sphere, rtol, atol, max_step, lambda_max, o);
+    integrate(&S, y0, rs + eps, r_sphere, rtol, atol, max_step, lambda_max, 0, o);
     const double* y = o->y;
     double sp = sin(y[5]), cp = cos(y[5]), R = y[3];
     double a = y[2] * cp - R * sp * y[4], b = y[2] * sp + R * cp * y[4]; /* tangent components along e1, e2 */
@@ -385,6 +441,8 @@ typedef struct {
     int64_t n;
     double M, r_sphere, rtol, atol, max_step, eps, lambda_max;
     int mode;
+    disk_t disk;
+    double *disk_xy;
     double *exit_pos, *exit_dir, *lam;
     int32_t *status, *nfev, *n_accept, *n_attempt;
     int64_t next; /* shared work counter, chunks of 64 rays */
@@ -400,7 +458,7 @@ static void* worker(void* arg) {
             ray_out_t o;
             if (J->mode == 0)
                 trace_parity(J->pos + 3 * i, J->dir + 3 * i, J->M, J->r_sphere, J->rtol, J->atol, J->max_step, J->eps,
-                             J->lambda_max, J->exit_pos + 3 * i, J->exit_dir + 3 * i, &o);
+                             J->lambda_max, &J->disk, J->exit_pos + 3 * i, J->exit_dir + 3 * i, &o);
             else
                 trace_plane(J->pos + 3 * i, J->dir + 3 * i, J->M, J->r_sphere, J->rtol, J->atol, J->max_step, J->eps,
                             J->lambda_max, J->exit_pos + 3 * i, J->exit_dir + 3 * i, &o);
@@ -409,6 +467,7 @@ static void* worker(void* arg) {
             if (J->n_accept) J->n_accept[i] = o.n_accept;
             if (J->n_attempt) J->n_attempt[i] = o.n_attempt;
             if (J->lam) J->lam[i] = o.lam;
+            if (J->disk_xy) { J->disk_xy[2 * i] = o.disk_xy[0]; J->disk_xy[2 * i + 1] = o.disk_xy[1]; }
         }
     }
     return 0;
@@ -419,12 +478,14 @@ int bhg_oracle_max_threads(void) {
     return c > 0 ? (int)c : 1;
 }
 
-/* C entry point (ctypes): AoS [n,3] in/out.  counters may be NULL.  nthreads<=0 -> all online cores. */
+/* C entry point (ctypes): AoS [n,3] in/out.  counters may be NULL.  nthreads<=0 -> all online cores.
+ * disk_xy (n x 2, may be NULL): first equatorial-plane crossing with disk_r_in <= r <= disk_r_out (parity mode). */
 int bhg_oracle_trace(const double* pos, const double* dir, int64_t n, double M, double r_sphere, double rtol,
                      double atol, double max_step, double eps_horizon, double lambda_max, int mode, int nthreads,
                      double* exit_pos, double* exit_dir, int32_t* status, int32_t* nfev, int32_t* n_accept,
-                     int32_t* n_attempt, double* lam) {
+                     int32_t* n_attempt, double* lam, double disk_r_in, double disk_r_out, double* disk_xy) {
     job_t J = {pos, dir, n, M, r_sphere, rtol, atol, max_step, eps_horizon, lambda_max, mode,
+               {disk_r_in, disk_xy ? disk_r_out : 0.0}, disk_xy,
                exit_pos, exit_dir, lam, status, nfev, n_accept, n_attempt, 0};
     if (nthreads <= 0) nthreads = bhg_oracle_max_threads();
     if (nthreads > 256) nthreads = 256;

@@ -143,7 +143,7 @@ def default_lambda_max(M, r_sphere):
 
 
 def trace_one(x0, k0, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, max_step=np.inf,
-              eps_horizon=0.01, lambda_max=None, return_sol=False):
+              eps_horizon=0.01, lambda_max=None, return_sol=False, disk=None):
     """One ray through real scipy solve_ivp.  Returns dict(exit_pos, exit_dir, status, nfev, n_accept, lam)."""
     from scipy.integrate import solve_ivp
 
@@ -154,7 +154,7 @@ def trace_one(x0, k0, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, max_step=np.in
     k0 = np.asarray(k0, dtype=np.float64)
     r0 = float(np.sqrt(np.dot(x0, x0)))
     out = dict(exit_pos=np.full(3, np.nan), exit_dir=np.full(3, np.nan), status=START_INSIDE_HOLE,
-               nfev=0, n_accept=0, lam=0.0)
+               nfev=0, n_accept=0, lam=0.0, disk_xy=np.full(2, np.nan))
     if not (r0 > rs + eps_horizon):  # inside (or on) the horizon event surface: nothing to integrate
         return out
     (r, th, ph), (k_r, k_th, k_ph) = xyz_to_sph(x0, k0)
@@ -190,9 +190,26 @@ def trace_one(x0, k0, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, max_step=np.in
         reached_end.direction = 1
         events.append(reached_end)
 
+    if disk is not None:
+        # equatorial-plane crossing z = r cos(theta) = 0 as a NON-terminal event on the same dense output: the
+        # continuous form of checkHitDisk's polyline scan (LimitedRelativisticRenderEngine.py:413-438)
+        def plane_crossing(lam, y):
+            return math.cos(y[5])
+
+        plane_crossing.terminal = False
+        plane_crossing.direction = 0
+        events.append(plane_crossing)
+
     with np.errstate(all="ignore"):
         res = solve_ivp(fun, (0.0, lambda_max), y0, method="RK45", events=events,
                         rtol=rtol, atol=atol, max_step=max_step)
+    if disk is not None:
+        r_in, r_out = disk
+        for tc, yc in zip(res.t_events[-1], res.y_events[-1]):
+            if r_in <= yc[3] <= r_out:   # first crossing inside the annulus (LIM.py:424)
+                st = math.sin(yc[5])
+                out["disk_xy"] = np.array([yc[3] * st * math.cos(yc[7]), yc[3] * st * math.sin(yc[7])])
+                break
     yE = res.y[:, -1]
     lam = float(res.t[-1])
     if res.status == 1:
@@ -218,7 +235,7 @@ def trace_one(x0, k0, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, max_step=np.in
 
 
 def trace(entry_pos, entry_dir, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, max_step=np.inf,
-          eps_horizon=0.01, lambda_max=None):
+          eps_horizon=0.01, lambda_max=None, disk=None):
     """Batched face of `trace_one` with the north-star signature (pure-Python loop; small N only)."""
     entry_pos = np.asarray(entry_pos, dtype=np.float64).reshape(-1, 3)
     entry_dir = np.asarray(entry_dir, dtype=np.float64).reshape(-1, 3)
@@ -228,10 +245,15 @@ def trace(entry_pos, entry_dir, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, max_
     status = np.empty(n, dtype=np.int32)
     nfev = np.empty(n, dtype=np.int32)
     n_accept = np.empty(n, dtype=np.int32)
+    disk_xy = np.empty((n, 2))
     for i in range(n):
-        o = trace_one(entry_pos[i], entry_dir[i], M, r_sphere, rtol, atol, max_step, eps_horizon, lambda_max)
+        o = trace_one(entry_pos[i], entry_dir[i], M, r_sphere, rtol, atol, max_step, eps_horizon, lambda_max,
+                      disk=disk)
         exit_pos[i], exit_dir[i], status[i] = o["exit_pos"], o["exit_dir"], o["status"]
         nfev[i], n_accept[i] = o["nfev"], o["n_accept"]
+        disk_xy[i] = o["disk_xy"]
+    if disk is not None:
+        return exit_pos, exit_dir, status, nfev, n_accept, disk_xy
     return exit_pos, exit_dir, status, nfev, n_accept
 
 
@@ -257,4 +279,4 @@ def trace_pool(entry_pos, entry_dir, processes, chunk=256, pool=None, **kw):
         if own:
             pool.close()
             pool.join()
-    return tuple(np.concatenate([p[j] for p in parts]) for j in range(5))
+    return tuple(np.concatenate([p[j] for p in parts]) for j in range(len(parts[0])))

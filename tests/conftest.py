@@ -47,19 +47,28 @@ def golden_kwargs(g):
 
 
 def assert_parity(got_pos, got_dir, got_status, ref_pos, ref_dir, ref_status, scale, exclude=None,
-                  pos_rtol=POS_RTOL, dir_atol=DIR_ATOL):
-    """Status bit-exact; exit position/direction within the stated tolerance for rays that terminated on an
-    event or at lambda_max.  `exclude` masks rays inside the stated critical band."""
+                  pos_rtol=POS_RTOL, dir_atol=DIR_ATOL, captured_tol=1e-3):
+    """Status bit-exact; exit position/direction within the stated tolerance for rays that left the sphere or
+    used up their affine length — the states the reference consumes (LIM.py:317-319, RRE.py:246).  The exit
+    state of a CAPTURED ray is never read by the reference (black pixel, LIM.py:308-309, RRE.py:242-244) and,
+    for rays that wind many times around the photon sphere before falling in, round-off is amplified beyond any
+    fixed bound (scipy vs its own C restatement differ by 1e-5 rad on such a ray), so it is only checked
+    loosely.  `exclude` masks rays inside the stated critical band."""
     got_status = np.asarray(got_status)
     ref_status = np.asarray(ref_status)
     keep = np.ones(len(ref_status), bool) if exclude is None else ~exclude
     bad = keep & (got_status != ref_status)
     assert not bad.any(), f"status mismatch on rays {np.nonzero(bad)[0][:10]}: {got_status[bad][:10]} vs {ref_status[bad][:10]}"
-    cmp = keep & np.isin(ref_status, (0, 1, 3))
+    cmp = keep & np.isin(ref_status, (0, 3))
     dpos = np.abs(got_pos[cmp] - ref_pos[cmp]).max(initial=0.0) / scale
     # angle between unit vectors
     cr = np.linalg.norm(np.cross(got_dir[cmp], ref_dir[cmp]), axis=1)
     ddir = cr.max(initial=0.0)
     assert dpos <= pos_rtol, f"exit position differs by {dpos:.3e} (relative to {scale})"
     assert ddir <= dir_atol, f"exit direction differs by {ddir:.3e} rad"
+    cap = keep & (ref_status == 1)
+    if cap.any():
+        cpos = np.abs(got_pos[cap] - ref_pos[cap]).max() / scale
+        cdir = np.linalg.norm(np.cross(got_dir[cap], ref_dir[cap]), axis=1).max()
+        assert cpos <= captured_tol and cdir <= captured_tol, f"captured-ray end state differs by {cpos:.2e} / {cdir:.2e}"
     return dpos, ddir

@@ -24,8 +24,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def run(pos, d, procs=8, **kw):
-    ep, ed, st, nfev, nacc = R.trace_pool(pos, d, procs, chunk=64, **kw)
-    return dict(entry_pos=pos, entry_dir=d, exit_pos=ep, exit_dir=ed, status=st, nfev=nfev, n_accept=nacc)
+    res = R.trace_pool(pos, d, procs, chunk=64, **kw)
+    ep, ed, st, nfev, nacc = res[:5]
+    out = dict(entry_pos=pos, entry_dir=d, exit_pos=ep, exit_dir=ed, status=st, nfev=nfev, n_accept=nacc)
+    if len(res) > 5:
+        out["disk_xy"] = res[5]
+    return out
 
 
 def save(name, data, **meta):
@@ -105,6 +109,13 @@ def main():
     e_pos, e_dir = np.array(e_pos, float), np.array(e_dir, float)
     ge = run(e_pos, e_dir, procs=1, lambda_max=80.0)
     save("edge_cases.npz", ge, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, lambda_max=80.0)
+
+    # equatorial disk crossing (checkHitDisk, LIM.py:413-438) as a non-terminal event: camera above the plane,
+    # annulus 6 M .. 20 M, plus near-critical 3-D rays (multiple plane crossings before capture / escape)
+    pd_, dd_ = raygen.config_bundle(40, 40, 1, jitter="mt19937", fov=0.55)
+    p5, d5, _ = raygen.near_critical_bundle(192, in_plane=False, seed=11)
+    gd = run(np.concatenate([pd_, p5]), np.concatenate([dd_, d5]), disk=(6.0, 20.0))
+    save("disk_crossing.npz", gd, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, disk_r_in=6.0, disk_r_out=20.0)
 
     # analytic known answers: deflection between sphere entry and exit
     bflat = np.array([5.3, 6.0, 8.0, 12.0, 20.0, 40.0])

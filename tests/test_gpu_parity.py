@@ -288,3 +288,36 @@ def test_sky_uv_mapping(api):
     esc = st2 == 0
     ref = np.stack([-np.arctan2(ed[:, 1], ed[:, 0]) / np.pi, 2 * (1 - np.arccos(ed[:, 2]) / np.pi) - 1], axis=1)
     assert np.abs(uv_h[esc] - ref[esc]).max() < 1.2e-7 and np.isnan(uv_h[st2 == 1]).all()
+
+
+def test_disk_crossing_event(api):
+    """SURVEY 8f row 2: first equatorial-plane crossing inside the annulus, located in flight on the dense output;
+    CUDA vs the scipy golden (non-terminal solve_ivp event) and, on a larger bundle, vs the C port."""
+    import torch
+    g = load_golden("disk_crossing.npz")
+    kw = golden_kwargs(g)
+    disk = (float(g["disk_r_in"]), float(g["disk_r_out"]))
+    ep, ed, st, dxy = api.trace(g["entry_pos"], g["entry_dir"], disk=disk, **kw)
+    band = crit_band(g["entry_pos"], g["entry_dir"], 1.0)
+    assert_parity(ep, ed, st, g["exit_pos"], g["exit_dir"], g["status"], 60.0, exclude=band)
+    hit = np.isfinite(g["disk_xy"][:, 0])
+    assert np.array_equal(np.isfinite(dxy[:, 0])[~band], hit[~band])
+    m = hit & ~band
+    assert np.abs(dxy[m] - g["disk_xy"][m]).max() / 20.0 < 1e-6
+    # the event never changes the integration itself
+    ep0, ed0, st0 = api.trace(g["entry_pos"], g["entry_dir"], **kw)
+    assert np.array_equal(ep, ep0, equal_nan=True) and np.array_equal(ed, ed0, equal_nan=True) and np.array_equal(st, st0)
+    # device entry, larger bundle, C port as checker
+    from blackhole_geodesic_calculator_b200 import raygen
+    from oracle import port
+    pos, d = raygen.config_bundle(256, 256, 1, jitter="philox")
+    out = api.trace(torch.from_numpy(pos).cuda(), torch.from_numpy(d).cuda(), disk=disk, image_width=256)
+    dxy_t = out[-1].cpu().numpy()
+    o = port.trace(pos, d, disk=disk)
+    band = crit_band(pos, d, 1.0)
+    hit = np.isfinite(o["disk_xy"][:, 0])
+    assert (np.isfinite(dxy_t[:, 0]) == hit)[~band].all() and hit.sum() > 1000
+    m = hit & ~band
+    assert np.abs(dxy_t[m] - o["disk_xy"][m]).max() / 20.0 < 1e-6
+    with pytest.raises(Exception):
+        api.trace(g["entry_pos"], g["entry_dir"], disk=disk, mode="plane")

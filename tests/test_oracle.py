@@ -86,3 +86,16 @@ def test_time_reversal():
     assert (back["status"] == 0).all()
     assert np.abs(back["exit_pos"] - g["entry_pos"][esc]).max() / 60.0 < 1e-6
     assert np.abs(back["exit_dir"] + g["entry_dir"][esc]).max() < 1e-6
+
+
+def test_port_disk_event_matches_scipy_golden():
+    """equatorial-plane crossing event (checkHitDisk, LIM.py:413-438) — C port vs scipy."""
+    g = load_golden("disk_crossing.npz")
+    kw = golden_kwargs(g)
+    o = port.trace(g["entry_pos"], g["entry_dir"], disk=(float(g["disk_r_in"]), float(g["disk_r_out"])), **kw)
+    assert np.array_equal(o["status"], g["status"]) and np.array_equal(o["nfev"], g["nfev"])
+    hit = np.isfinite(g["disk_xy"][:, 0])
+    assert np.array_equal(np.isfinite(o["disk_xy"][:, 0]), hit) and hit.sum() > 100
+    assert np.abs(o["disk_xy"][hit] - g["disk_xy"][hit]).max() < 1e-7
+    R = np.linalg.norm(g["disk_xy"][hit], axis=1)
+    assert (R >= 6.0).all() and (R <= 20.0).all()
