@@ -195,10 +195,16 @@ def run_b200(args):
     params = api.make_params(mode=args.mode, refill_threshold=args.threshold, image_width=0 if args.no_tiles else W)
     stream = torch.cuda.current_stream(dev)
 
+    extras = None
+    if args.disk:  # opt-in in-flight disk-crossing event (next-row 2), annulus 6 M .. 20 M
+        from blackhole_geodesic_calculator_b200._lib import BhgExtras
+        disk_xy = torch.empty((n, 2), dtype=torch.float64, device=dev)
+        extras = BhgExtras(6.0, 20.0, disk_xy.data_ptr())
+
     def step(with_counters=False):
         api.trace_device(pos.data_ptr(), d.data_ptr(), exit_pos.data_ptr(), exit_dir.data_ptr(), status.data_ptr(),
                          counters.data_ptr() if with_counters else None, None, n, api.LAYOUT_AOS, params, local,
-                         stream.cuda_stream)
+                         stream.cuda_stream, extras)
 
     def barrier():
         if world > 1:
@@ -322,7 +328,7 @@ def run_b200(args):
                                    "seed 42; at N>1 rank r integrates animation frame r (config 4, camera azimuth "
                                    "+3.6 deg/frame)",
                        "mode": args.mode, "refill_threshold": args.threshold or 32,
-                       "image_width_hint": 0 if args.no_tiles else W,
+                       "image_width_hint": 0 if args.no_tiles else W, "disk_event": bool(args.disk),
                        "rays_per_step_per_gpu": n, "cache": "inputs+outputs 525 MB per step > 126 MB L2 (no flush)",
                        "mean_attempts_per_ray": att / n},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": n * 48, "d2h_bytes_per_step": n * 52,
@@ -385,6 +391,7 @@ def main():
     ap.add_argument("--threshold", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tiles", action="store_true", help="do not pass the image_width scheduling hint")
+    ap.add_argument("--disk", action="store_true", help="also locate equatorial-disk crossings (6 M .. 20 M) in flight")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -405,8 +405,13 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
                         if constexpr (DISK) {  // non-terminal plane-crossing event on this accepted step
                             if (!disk_hit) {
                                 const double half_pi = 1.57079632679489661923, inv_pi = 0.31830988618379067154;
-                                if (floor((x[2] - half_pi) * inv_pi) != floor((xn[2] - half_pi) * inv_pi))
-                                    disk_hit = disk_crossing(a, idx, k, x, K, h, 1.0);
+                                if (floor((x[2] - half_pi) * inv_pi) != floor((xn[2] - half_pi) * inv_pi)) {
+                                    // cheap radial reject before the (divergent) root search: within the step
+                                    // r stays inside [min(r0,r1) - mg, max(r0,r1) + mg], mg = |h| max|k_r|
+                                    const double mg = fabs(h) * fmax(fabs(k[1]), fabs(kn[1]));
+                                    if (fmin(x[1], xn[1]) - mg <= a.disk_r_out && fmax(x[1], xn[1]) + mg >= a.disk_r_in)
+                                        disk_hit = disk_crossing(a, idx, k, x, K, h, 1.0);
+                                }
                             }
                         }
                         h_abs *= factor;
