@@ -378,20 +378,23 @@ __device__ __forceinline__ double initial_step(const double (&k)[NK], const doub
                                                double rs, double rtol, double atol, double interval,
                                                double max_step) {
     if (interval == 0.0) return 0.0;
+    // scale_i = atol + |y_i| rtol; one reciprocal per (momentum, position) pair
     double isk[NK], isx[NK];
-    double d0 = 0.0, d1 = 0.0;
+    double D0 = 0.0, D1 = 0.0;  // sums of squares: d0^2 = D0 / (2 NK), d1^2 = D1 / (2 NK)
 #pragma unroll
     for (int i = 0; i < NK; i++) {
-        isk[i] = fast_rcp5(fma(fabs(k[i]), rtol, atol));
-        isx[i] = fast_rcp5(fma(fabs(x[i]), rtol, atol));
+        const double sk = fma(fabs(k[i]), rtol, atol), sx = fma(fabs(x[i]), rtol, atol);
+        const double inv = fast_rcp5(sk * sx);
+        isk[i] = inv * sx;
+        isx[i] = inv * sk;
         const double a = k[i] * isk[i], b = x[i] * isx[i];
         const double c = K0[i] * isk[i], d = k[i] * isx[i];
-        d0 = fma(a, a, fma(b, b, d0));
-        d1 = fma(c, c, fma(d, d, d1));
+        D0 = fma(a, a, fma(b, b, D0));
+        D1 = fma(c, c, fma(d, d, D1));
     }
-    d0 = sqrt(d0 / (2 * NK));
-    d1 = sqrt(d1 / (2 * NK));
-    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+    const double n2 = 2.0 * NK;
+    // h0 = 0.01 d0 / d1 unless d0 < 1e-5 or d1 < 1e-5  (common.py:117-120), on the squares
+    double h0 = (D0 < 1e-10 * n2 || D1 < 1e-10 * n2) ? 1e-6 : 0.01 * sqrt(D0 * fast_rcp5(D1));
     h0 = fmin(h0, interval);
     double k1[NK], x1[NK], F1[NK];
 #pragma unroll
@@ -400,19 +403,22 @@ __device__ __forceinline__ double initial_step(const double (&k)[NK], const doub
         x1[i] = fma(h0, k[i], x[i]);
     }
     Rhs<NK>::eval(k1, x1, rs, F1);
-    double d2 = 0.0;
+    double D2 = 0.0;
 #pragma unroll
     for (int i = 0; i < NK; i++) {
         const double a = (F1[i] - K0[i]) * isk[i];
         const double b = (k1[i] - k[i]) * isx[i];
-        d2 = fma(a, a, fma(b, b, d2));
+        D2 = fma(a, a, fma(b, b, D2));
     }
-    d2 = sqrt(d2 / (2 * NK)) / h0;
+    // d1^2 and d2^2 = D2 / (2 NK h0^2); h1 = (0.01 / max(d1, d2))^(1/5) = (max(d1,d2)^2 * 1e4)^(-1/10)
+    const double ih0 = fast_rcp5(h0);
+    const double d1sq = D1 / n2, d2sq = (D2 / n2) * (ih0 * ih0);
+    const double msq = fmax(d1sq, d2sq);
     double h1;
-    if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
+    if (!(msq > 1e-30)) h1 = fmax(1e-6, h0 * 1e-3);  // d1 <= 1e-15 and d2 <= 1e-15
     else {
-        const double arg = 0.01 / fmax(d1, d2);
-        h1 = (arg > 1e-30 && arg < 1e30) ? fifth_root(arg) : pow(arg, 0.2);
+        const double arg = msq * 1e4;
+        h1 = (arg > 1e-30 && arg < 1e30) ? inv_tenth_root(arg) : pow(arg, -0.1);
     }
     return fmin(fmin(100.0 * h0, h1), fmin(interval, max_step));
 }
@@ -442,6 +448,45 @@ __device__ __forceinline__ void dense_coeffs_x(double ki, double K0, double K1, 
     q[3] = fma(h, s3, TAB(PS3) * ki);
 }
 
+// Shared-weight form for evaluating many components at one s: y_i(s) = y_i + h sum_j w_j(s) K_j[i] with
+//   momentum:  w_j = sum_c P[j][c] s^(c+1)                     (7 weights, j = 1 has P = 0)
+//   position:  x_i(s) = x_i + h (k_i ps(s) + h sum_l v_l(s) K_l[i]),  v_l = sum_c PA[l][c] s^(c+1), ps = sum_c PS[c] s^(c+1)
+struct DenseWeights {
+    double wk[7];  // wk[1] unused
+    double vx[6];
+    double ps;
+};
+
+__device__ __forceinline__ void dense_weights(double s, DenseWeights& w) {
+    const double s2 = s * s;
+    w.wk[0] = fma(s2, fma(s, fma(s, TAB(P13), TAB(P12)), TAB(P11)), s);
+    w.wk[1] = 0.0;
+    w.wk[2] = s2 * fma(s, fma(s, TAB(P33), TAB(P32)), TAB(P31));
+    w.wk[3] = s2 * fma(s, fma(s, TAB(P43), TAB(P42)), TAB(P41));
+    w.wk[4] = s2 * fma(s, fma(s, TAB(P53), TAB(P52)), TAB(P51));
+    w.wk[5] = s2 * fma(s, fma(s, TAB(P63), TAB(P62)), TAB(P61));
+    w.wk[6] = s2 * fma(s, fma(s, TAB(P73), TAB(P72)), TAB(P71));
+    w.vx[0] = s * fma(s, fma(s, fma(s, TAB(PA13), TAB(PA12)), TAB(PA11)), TAB(PA10));
+    w.vx[1] = s * fma(s, fma(s, fma(s, TAB(PA23), TAB(PA22)), TAB(PA21)), TAB(PA20));
+    w.vx[2] = s * fma(s, fma(s, fma(s, TAB(PA33), TAB(PA32)), TAB(PA31)), TAB(PA30));
+    w.vx[3] = s * fma(s, fma(s, fma(s, TAB(PA43), TAB(PA42)), TAB(PA41)), TAB(PA40));
+    w.vx[4] = s * fma(s, fma(s, fma(s, TAB(PA53), TAB(PA52)), TAB(PA51)), TAB(PA50));
+    w.vx[5] = s * fma(s, fma(s, fma(s, TAB(PA63), TAB(PA62)), TAB(PA61)), TAB(PA60));
+    w.ps = s * fma(s, fma(s, fma(s, TAB(PS3), TAB(PS2)), TAB(PS1)), 1.0);
+}
+
+__device__ __forceinline__ double dense_k(const DenseWeights& w, double ki, double K0, double K2, double K3, double K4,
+                                          double K5, double K6, double h) {
+    const double acc = fma(w.wk[6], K6, fma(w.wk[5], K5, fma(w.wk[4], K4, fma(w.wk[3], K3, fma(w.wk[2], K2, w.wk[0] * K0)))));
+    return fma(h, acc, ki);
+}
+
+__device__ __forceinline__ double dense_x(const DenseWeights& w, double xi, double ki, double K0, double K1, double K2,
+                                          double K3, double K4, double K5, double h) {
+    const double acc = fma(w.vx[5], K5, fma(w.vx[4], K4, fma(w.vx[3], K3, fma(w.vx[2], K2, fma(w.vx[1], K1, w.vx[0] * K0)))));
+    return fma(h, fma(h, acc, ki * w.ps), xi);
+}
+
 __device__ __forceinline__ double dense_eval(const double (&q)[4], double yold, double h, double s) {
     // same term order as numpy: p = cumprod([s,s,s,s]); y = h * dot(Q, p) + y_old
     const double p2 = s * s, p3 = p2 * s, p4 = p3 * s;
@@ -449,25 +494,29 @@ __device__ __forceinline__ double dense_eval(const double (&q)[4], double yold, 
     return fma(h, acc, yold);
 }
 
-// Root of r(s) - target on s in [0,1] given a sign change between the end points.
+// Root of r(s) - target on s in [0, s_hi] given a sign change between the end points.
 // scipy uses brentq(xtol=rtol=4 eps) on the same quartic (ivp.py:52-77); any bracketing method that
-// converges to the last bit of s lands inside brentq's own tolerance.  Newton with bisection safeguard.
+// converges to the last bit of s lands inside brentq's own tolerance.  Halley iteration (cubic: typically
+// 3 iterations from the secant start) with a bisection safeguard on the maintained bracket.
 __device__ __forceinline__ double event_root(const double (&q)[4], double rold, double h, double target,
                                              double s_hi = 1.0) {
     double lo = 0.0, hi = s_hi;
-    double flo = rold - target;
-    double fhi = dense_eval(q, rold, h, s_hi) - target;
+    const double flo = rold - target;
+    const double fhi = dense_eval(q, rold, h, s_hi) - target;
     if (flo == 0.0) return 0.0;
     if (fhi == 0.0) return s_hi;
     const bool lo_neg = flo < 0.0;
-    double s = s_hi * (flo / (flo - fhi));  // secant start
+    double s = s_hi * (flo * fast_rcp5(flo - fhi));  // secant start
     if (!(s > 0.0 && s < s_hi)) s = 0.5 * s_hi;
-    for (int it = 0; it < 80; it++) {
+    const double q1x2 = 2.0 * q[1], q2x3 = 3.0 * q[2], q3x4 = 4.0 * q[3], q2x6 = 6.0 * q[2], q3x12 = 12.0 * q[3];
+    for (int it = 0; it < 60; it++) {
         const double fs = dense_eval(q, rold, h, s) - target;
         if (fs == 0.0) return s;
         if ((fs < 0.0) == lo_neg) lo = s; else hi = s;
-        const double dfs = h * fma(4.0 * q[3], s * s * s, fma(3.0 * q[2], s * s, fma(2.0 * q[1], s, q[0])));
-        double sn = fma(-fs, fast_rcp(dfs), s);
+        const double d1 = h * fma(s, fma(s, fma(s, q3x4, q2x3), q1x2), q[0]);  // f'
+        const double d2 = h * fma(s, fma(s, q3x12, q2x6), q1x2);               // f''
+        const double den = fma(2.0 * d1, d1, -fs * d2);
+        double sn = fma(-2.0 * fs * d1, fast_rcp5(den), s);
         if (!(sn > lo && sn < hi)) sn = 0.5 * (lo + hi);
         if (fabs(sn - s) <= 2.220446049250313e-16 * fmax(fabs(sn), 1e-3) || hi - lo <= 4.4e-16 * hi) return sn;
         s = sn;

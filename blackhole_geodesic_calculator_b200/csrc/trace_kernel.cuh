@@ -119,16 +119,19 @@ __device__ __forceinline__ bool init_state<4>(const double (&x0)[3], const doubl
     const double r2 = fma(x0[2], x0[2], rho2);
     const double r = sqrt(r2), rho = sqrt(rho2);
     if (!(r > r_hor)) return false;
-    const double th = acos(x0[2] / r);
+    // reciprocals instead of IEEE divisions (fast_rcp5 is bit-identical to 1/a on the B200 self-test sweep;
+    // a zero denominator — entry on the polar axis — still yields a non-finite state, i.e. STEP_FAILED)
+    const double ir = fast_rcp5(r);
+    const double th = acos(x0[2] * ir);
     const double ph = atan2(x0[1], x0[0]);
     const double xk = fma(x0[0], k0[0], x0[1] * k0[1]);
-    const double k_r = fma(x0[2], k0[2], xk) / r;
-    const double k_th = fma(x0[2], xk, -rho2 * k0[2]) / (r2 * rho);
-    const double k_ph = fma(x0[0], k0[1], -x0[1] * k0[0]) / rho2;
-    const double s = sin(th);
+    const double k_r = fma(x0[2], k0[2], xk) * ir;
+    const double k_th = fma(x0[2], xk, -rho2 * k0[2]) * fast_rcp5(r2 * rho);
+    const double k_ph = fma(x0[0], k0[1], -x0[1] * k0[0]) * fast_rcp5(rho2);
+    const double s2 = rho2 * (ir * ir);  // sin^2(theta)
     const double rm = r - rs;
     // null condition g_mn k^m k^n = 0, future-directed root (time_like=False, RelativisticRenderEngine.py:134)
-    const double k_t = r * sqrt(fma(k_r, k_r, rm * r * fma(k_ph * k_ph * s, s, k_th * k_th))) / rm;
+    const double k_t = r * sqrt(fma(k_r, k_r, rm * r * fma(k_ph * k_ph, s2, k_th * k_th))) * fast_rcp5(rm);
     k[0] = k_t; k[1] = k_r; k[2] = k_th; k[3] = k_ph;
     x[0] = 0.0; x[1] = r; x[2] = th; x[3] = ph;
     return true;
@@ -186,7 +189,7 @@ __device__ __forceinline__ void exit_state<4>(const double (&k)[4], const double
     v[0] = fma(a, cp, -b * sp);
     v[1] = fma(a, sp, b * cp);
     v[2] = fma(k_r, ct, -R * st * k_th);
-    const double inv = 1.0 / sqrt(fma(v[0], v[0], fma(v[1], v[1], v[2] * v[2])));
+    const double inv = rsqrt(fma(v[0], v[0], fma(v[1], v[1], v[2] * v[2])));
 #pragma unroll
     for (int c = 0; c < 3; c++) ko[c] = v[c] * inv;
 }
@@ -201,7 +204,7 @@ __device__ __forceinline__ void exit_state<3>(const double (&k)[3], const double
     const double R = x[1];
     const double a = fma(k[1], cp, -R * sp * k[2]);
     const double b = fma(k[1], sp, R * cp * k[2]);
-    const double inv = 1.0 / sqrt(fma(a, a, b * b));
+    const double inv = rsqrt(fma(a, a, b * b));
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         xo[c] = R * fma(cp, e1[c], sp * e2[c]);
@@ -306,13 +309,14 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
                     if constexpr (DISK) {  // crossings before the terminal root still count
                         if (!disk_hit) disk_hit = disk_crossing(a, idx, k, x, K, h, s);
                     }
+                    // dense output at the event (rk.py:715-738); k_t and t are not needed by the exit conversion
+                    DenseWeights w;
+                    dense_weights(s, w);
 #pragma unroll
-                    for (int i = 0; i < NK; i++) {
-                        double qk[4], qx[4];
-                        dense_coeffs_x(k[i], K[0][i], K[1][i], K[2][i], K[3][i], K[4][i], K[5][i], h, qx);
-                        dense_coeffs_k(K[0][i], K[2][i], K[3][i], K[4][i], K[5][i], K[6][i], qk);
-                        x[i] = dense_eval(qx, x[i], h, s);
-                        k[i] = dense_eval(qk, k[i], h, s);
+                    for (int i = 1; i < NK; i++) {
+                        const double xi = dense_x(w, x[i], k[i], K[0][i], K[1][i], K[2][i], K[3][i], K[4][i], K[5][i], h);
+                        k[i] = dense_k(w, k[i], K[0][i], K[2][i], K[3][i], K[4][i], K[5][i], K[6][i], h);
+                        x[i] = xi;
                     }
                     t = fma(s, h, t);
                 }
