@@ -75,19 +75,26 @@ __device__ __forceinline__ double fast_rcp(double a) {
 // (|d| ~ 10 e0) the exact answer is x0 (1 + d)^(-1/10) = x0 (1 - d/10 + 11 d^2/200 - 77 d^3/2000 + ...); the
 // truncation error 0.03 d^4 is < 1e-18 for |d| < 1e-4.  Dependency depth 9 instead of 14 for two Newton steps
 // (this sits on the serial path between two attempts).  One Newton step follows only if the seed was poor.
+__device__ __noinline__ double pow_cold(double a, double e) { return pow(a, e); }  // cold fallback, one copy
+
+// 2^(e * log2(a)) in FP32 on the MUFU unit (lg2.approx / ex2.approx: relative error ~1e-6), as a double
+__device__ __forceinline__ double pow_seed(double a, float e) {
+    float l, r;
+    const float af = (float)a;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(af));
+    l *= e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(l));
+    return (double)r;
+}
+
 __device__ __forceinline__ double inv_tenth_root(double a) {
-    float af = (float)a;
-    double x = (double)exp2f(-0.1f * log2f(af));
-    double x2 = x * x;
-    double x4 = x2 * x2;
-    double x5 = x4 * x;
-    double d = fma(a, x5 * x5, -1.0);
-    if (fabs(d) > 1e-4) {  // never taken with the hardware lg2/ex2 (seed error ~1e-6); keeps the bound honest
-        x = x * fma(-0.1, d, 1.0);
-        x2 = x * x; x4 = x2 * x2; x5 = x4 * x;
-        d = fma(a, x5 * x5, -1.0);
-    }
-    const double p = fma(d, fma(d, fma(d, -0.0385, 0.055), -0.1), 0.0);
+    const double x = pow_seed(a, -0.1f);
+    const double x2 = x * x;
+    const double x4 = x2 * x2;
+    const double x8 = x4 * x4;
+    const double d = fma(a, x8 * x2, -1.0);
+    if (!(fabs(d) < 1e-4)) return pow_cold(a, -0.1);  // seed worse than 1e-5 (never with the MUFU seed); also NaN
+    const double p = d * fma(d, fma(d, -0.0385, 0.055), -0.1);
     return fma(x, p, x);
 }
 
@@ -104,8 +111,7 @@ __device__ __forceinline__ double abs_max(double a, double b) {
 // a^(1/5) for a in [1e-30, 1e30] (initial-step heuristic): Newton on x^-5 = a for the inverse root, then
 // a * x^4.  Float seed 1e-5 -> two steps -> 1e-18.
 __device__ __forceinline__ double fifth_root(double a) {
-    float af = (float)a;
-    double x = (double)exp2f(-0.2f * log2f(af));
+    double x = pow_seed(a, -0.2f);
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         double x2 = x * x;
@@ -175,18 +181,17 @@ struct Rhs<4> {
         const double i_s = inv * p;           // 1 / sin th
         const double i_rrm = inv * s;         // 1 / (r (r - rs))
         const double i_r = i_rrm * rm;        // 1 / r
-        const double A = rs * i_rrm;          // rs / (r (r - rs))
-        const double hA = 0.5 * A;
+        const double hA = (0.5 * rs) * i_rrm; // rs / (2 r (r - rs))   (0.5 rs is loop-invariant)
         const double kph2s = (kph * kph) * s;
         const double ang = fma(kph2s, s, kth * kth);  // k_th^2 + k_ph^2 sin^2
         const double q = rm * i_r;                    // (r - rs) / r
         const double w = (hA * q) * q;                // rs (r - rs) / (2 r^3)
         const double kr_r = kr * i_r;
-        const double m2kph = -2.0 * kph;
-        f[0] = -(A * kr) * kt;
-        f[1] = fma(hA * kr, kr, fma(-w * kt, kt, rm * ang));
+        const double hAkr = hA * kr;
+        f[0] = (-2.0 * hAkr) * kt;
+        f[1] = fma(hAkr, kr, fma(-w * kt, kt, rm * ang));
         f[2] = fma(kr_r * kth, -2.0, kph2s * c);
-        f[3] = m2kph * fma(kth, c * i_s, kr_r);
+        f[3] = (-2.0 * kph) * fma(kth, c * i_s, kr_r);
     }
 };
 
@@ -199,13 +204,13 @@ struct Rhs<3> {
         const double rm = r - rs;
         const double i_rrm = fast_rcp(r * rm);
         const double i_r = i_rrm * rm;
-        const double A = rs * i_rrm;
-        const double hA = 0.5 * A;
+        const double hA = (0.5 * rs) * i_rrm;
         const double q = rm * i_r;
         const double w = (hA * q) * q;
-        f[0] = -(A * kr) * kt;
-        f[1] = fma(hA * kr, kr, fma(-w * kt, kt, rm * (kph * kph)));
-        f[2] = -2.0 * kph * (kr * i_r);
+        const double hAkr = hA * kr;
+        f[0] = (-2.0 * hAkr) * kt;
+        f[1] = fma(hAkr, kr, fma(-w * kt, kt, rm * (kph * kph)));
+        f[2] = (-2.0 * kph) * (kr * i_r);
     }
 };
 
