@@ -93,9 +93,12 @@ __device__ __forceinline__ double inv_tenth_root(double a) {
     const double x4 = x2 * x2;
     const double x8 = x4 * x4;
     const double d = fma(a, x8 * x2, -1.0);
-    if (!(fabs(d) < 1e-4)) return pow_cold(a, -0.1);  // seed worse than 1e-5 (never with the MUFU seed); also NaN
     const double p = d * fma(d, fma(d, -0.0385, 0.055), -0.1);
-    return fma(x, p, x);
+    double res = fma(x, p, x);
+    // seed worse than 1e-5 (never with the MUFU seed) or NaN: cold library fallback.  Tested after the result is
+    // formed so that the compare overlaps the polynomial instead of sitting on the serial path.
+    if (!(fabs(d) < 1e-4)) res = pow_cold(a, -0.1);
+    return res;
 }
 
 // max(|a|, |b|) on the integer pipe: for finite doubles the order of |x| is the order of its bit pattern.
@@ -360,12 +363,15 @@ __device__ __forceinline__ double rk45_attempt(const double (&k)[NK], const doub
     return esum;
 }
 
-// step-size factor 0.9 * err^(-1/5) clipped to [lo, hi], with err^2 = en2 (scipy/_ivp/rk.py:148-163)
-__device__ __forceinline__ double step_factor(double en2, double lo, double hi) {
-    if (!(en2 < 1e8)) return lo;   // huge, inf or NaN error norm
-    if (en2 < 1e-12) return hi;    // includes en2 == 0
-    double f = 0.9 * inv_tenth_root(en2);
-    return fmin(hi, fmax(lo, f));
+// step-size factors 0.9 * err^(-1/5), with err^2 = en2 (scipy/_ivp/rk.py:148-163).  Branch-free clamps: the
+// caller already knows whether the step was accepted (en2 < 1) or rejected (en2 >= 1 or NaN).
+//   accepted: min(hi, 0.9 err^-0.2), hi = 10 (or 1 after a rejection); en2 -> 0 gives hi (0.9 (1e-12)^-0.1 = 14.3)
+__device__ __forceinline__ double step_factor_accept(double en2, double hi) {
+    return fmin(hi, 0.9 * inv_tenth_root(fmax(en2, 1e-12)));
+}
+//   rejected: max(0.2, 0.9 err^-0.2); huge / inf / NaN error norms give 0.2 (fmin drops the NaN; 0.9 (1e8)^-0.1 = 0.14)
+__device__ __forceinline__ double step_factor_reject(double en2) {
+    return fmax(0.2, 0.9 * inv_tenth_root(fmin(en2, 1e8)));
 }
 
 // 10 * |nextafter(t, +inf) - t|  for t >= 0 (scipy/_ivp/rk.py:119)

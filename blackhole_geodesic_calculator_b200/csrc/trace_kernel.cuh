@@ -396,7 +396,7 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
                 const double en2 = esum * (1.0 / (2 * NK));  // (RMS error norm)^2 over all 2 NK components
                 if (en2 < 1.0) {
                     n_accept++;
-                    const double factor = step_factor(en2, 0.2, rejected ? 1.0 : 10.0);
+                    const double factor = step_factor_accept(en2, rejected ? 1.0 : 10.0);
                     // events on the accepted step (ivp.py:134-158): horizon either direction, sphere upward
                     const double gh0 = x[IR] - a.r_hor, gh1 = xn[IR] - a.r_hor;
                     const double ge0 = x[IR] - a.r_sphere, ge1 = xn[IR] - a.r_sphere;
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
                         if (t - t_bound >= 0.0) state = LAMBDA_EXHAUSTED;
                     }
                 } else {
-                    h_abs *= step_factor(en2, 0.2, 10.0);
+                    h_abs *= step_factor_reject(en2);
                     rejected = true;
                 }
             }
