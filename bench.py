@@ -327,7 +327,7 @@ def run_b200(args):
                                    "r_sphere=60M, rtol=1e-3, atol=1e-6, camera (120,-80,40)M fov 0.6, Philox jitter "
                                    "seed 42; at N>1 rank r integrates animation frame r (config 4, camera azimuth "
                                    "+3.6 deg/frame)",
-                       "mode": args.mode, "refill_threshold": args.threshold or 32,
+                       "mode": args.mode, "refill_threshold": args.threshold or "adaptive (idle budget 96 lane-iterations)",
                        "image_width_hint": 0 if args.no_tiles else W, "disk_event": bool(args.disk),
                        "rays_per_step_per_gpu": n, "cache": "inputs+outputs 525 MB per step > 126 MB L2 (no flush)",
                        "mean_attempts_per_ray": att / n},

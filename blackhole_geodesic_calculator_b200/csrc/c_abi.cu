@@ -164,7 +164,13 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
     a.has_outer = std::isfinite(p->r_sphere) ? 1 : 0;
     a.rtol = p->rtol; a.atol = p->atol; a.max_step = p->max_step;
     a.lambda_max = p->lambda_max > 0.0 ? p->lambda_max : 10.0 * p->r_sphere;
-    a.refill_threshold = p->refill_threshold > 0 ? p->refill_threshold : 32;
+    // refill policy: explicit lane threshold, else the adaptive idle budget (lane-iterations per service)
+    a.refill_threshold = p->refill_threshold;
+    a.idle_budget = 96;  // measured optimum across coherent and incoherent workloads (profiles/r1i_refill_policy.txt)
+    if (const char* e = getenv("BHG_IDLE_BUDGET")) {
+        int v = atoi(e);
+        if (v > 0) a.idle_budget = v;
+    }
     a.tile_width = (image_width > 0 && image_width % 8 == 0 && n % (4LL * image_width) == 0 && !order) ? image_width : 0;
     if (disk) { a.disk_r_in = ex->disk_r_in; a.disk_r_out = ex->disk_r_out; a.disk_xy = ex->disk_xy; }
     unsigned slot = c.next_slot.fetch_add(1) % kQueueSlots;

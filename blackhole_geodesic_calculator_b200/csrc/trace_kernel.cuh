@@ -31,7 +31,10 @@ struct TraceArgs {
     long long n;
     double rs, r_hor, r_sphere, rtol, atol, max_step, lambda_max;
     int has_outer;
-    int refill_threshold;
+    int refill_threshold;  // > 0: service when this many lanes are idle
+    int idle_budget;       // used when refill_threshold == 0: service when the idle lane-iterations accumulated
+                           // since the last service reach this budget ("ski rental": idle until the waste equals
+                           // the price of one service), which adapts to coherent and incoherent batches alike
     int tile_width;  // > 0: queue slots enumerate 8 x 4 pixel tiles of a row-major image of this width
     // DISK variant only: first crossing of the equatorial plane with disk_r_in <= r <= disk_r_out
     double disk_r_in, disk_r_out;
@@ -271,6 +274,8 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
     bool disk_hit = false;
     bool exhausted = false;  // warp-uniform: queue has no more rays
     const int T = a.refill_threshold;
+    const int B = a.idle_budget;
+    int idle_acc = 0;  // warp-uniform
     const double t_bound = a.lambda_max;
 
 #pragma unroll
@@ -289,10 +294,13 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
             if (running == 0u && pending == 0u) break;
             service = (running == 0u);  // drain: finish everybody together at the very end
         } else {
-            service = (running == 0u) || (__popc(~running) >= T);
+            const int n_idle = __popc(~running);
+            idle_acc += n_idle;
+            service = (running == 0u) || (T > 0 ? n_idle >= T : idle_acc >= B);
         }
 
         if (service) {
+            idle_acc = 0;
             // ---------------- finish pending lanes ----------------
             if (state != LANE_RUNNING && state != LANE_EMPTY) {
                 int final_status = state;

@@ -70,7 +70,8 @@ typedef struct bhg_params {
     double eps_horizon; /* capture event at r = r_s + eps_horizon                          */
     double lambda_max;  /* affine-length bound (curve_end, RRE.py:61,294); <= 0 selects 10 r_sphere */
     int32_t mode;       /* enum bhg_mode                                                   */
-    int32_t refill_threshold; /* warp work queue: idle lanes that trigger a refill, 1..32; 0 = default */
+    int32_t refill_threshold; /* warp work queue: idle lanes that trigger a refill, 1..32; 0 = adaptive (default):
+                                 refill once the idle lane-iterations since the last refill reach a fixed budget */
     int32_t image_width;      /* coherence hint: the rays are a row-major image (or stack of images) of this
                                  width, as the reference's s -> y -> x loop produces them (RRE.py:195-218); the
                                  queue then hands every warp an 8 x 4 pixel tile instead of 32 pixels of one row.
