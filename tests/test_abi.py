@@ -89,3 +89,24 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
                 assert "rk45_port" not in text or f.endswith(".md"), f
+
+
+def test_maximum_size_is_rejected_before_any_buffer_is_touched():
+    """n beyond 2^31 - 1 rays per call is refused by validation (no device, no buffers needed)."""
+    lib = _lib.load()
+    p = api.make_params()
+    rc = lib.bhg_trace_schwarzschild_f64(None, None, None, None, None, None, None, 2**31, 1, ctypes.byref(p), 0, None)
+    assert rc == -1 and b"exceeds" in lib.bhg_last_error_string()
+    rc = lib.bhg_trace_schwarzschild_f64_host(None, None, None, None, None, None, -5, ctypes.byref(p), 0)
+    assert rc == -1 and b"negative" in lib.bhg_last_error_string()
+
+
+def test_camera_validation_needs_no_gpu():
+    import numpy as np
+    cam = api.make_camera((120.0, -80.0, 40.0), np.eye(3), 0, 16)
+    lib = _lib.load()
+    p = api.make_params()
+    rc = lib.bhg_trace_camera_f64_host(ctypes.byref(cam), None, None, None, None, 16, ctypes.byref(p), 0)
+    assert rc == -1 and b"width/height" in lib.bhg_last_error_string()
+    with pytest.raises(ValueError):
+        api.make_camera((1, 2, 3), np.eye(3), 8, 8, jitter="mt19937")
