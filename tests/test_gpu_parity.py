@@ -321,3 +321,41 @@ def test_disk_crossing_event(api):
     assert np.abs(dxy_t[m] - o["disk_xy"][m]).max() / 20.0 < 1e-6
     with pytest.raises(Exception):
         api.trace(g["entry_pos"], g["entry_dir"], disk=disk, mode="plane")
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_randomised_parameters_against_c_port(api, seed):
+    """Random mass / sphere radius / tolerances / max_step / lambda_max / horizon offset, camera bundles from random
+    directions (inside and outside the sphere): CUDA vs the C restatement, both modes."""
+    from blackhole_geodesic_calculator_b200 import raygen
+    from oracle import port
+    rng = np.random.default_rng(seed)
+    M = float(rng.uniform(0.3, 3.0))
+    R = float(rng.uniform(12.0, 90.0)) * M
+    rtol = float(10.0 ** rng.uniform(-8, -3))
+    atol = float(rtol * 10.0 ** rng.uniform(-4, -2))
+    max_step = float(rng.choice([np.inf, np.inf, 5.0 * M, 20.0 * M]))
+    eps = float(rng.choice([0.01, 0.05, 0.001])) * M
+    lam = float(rng.choice([0.0, 0.0, 3.0 * R]))  # 0 -> default 10 R
+    cam = rng.normal(size=3)
+    cam *= rng.uniform(1.3, 3.0) * R / np.linalg.norm(cam)
+    half = math_asin(R / np.linalg.norm(cam))
+    rot = raygen.look_at_rotation(tuple(cam))
+    d = raygen.camera_rays(48, 32, 1, 1.2 * half, 1.2 * half, rot, seed, "philox")
+    pos, hit = raygen.sphere_entry(cam, d, R)
+    pos, d = pos[hit], d[hit]
+    kw = dict(M=M, r_sphere=R, rtol=rtol, atol=atol, max_step=max_step, eps_horizon=eps,
+              lambda_max=None if lam == 0.0 else lam)
+    for mode, pmode in (("parity", 0), ("plane", 1)):
+        ep, ed, st, cnt = api.trace(pos, d, mode=mode, return_counters=True, **kw)
+        o = port.trace(pos, d, mode=pmode, **kw)
+        b = raygen.conserved_impact_parameter(pos, d, M)
+        band = np.abs(b - B_CRIT * M) <= B_CRIT_BAND * M
+        assert_parity(ep, ed, st, o["exit_pos"], o["exit_dir"], o["status"], R, exclude=band)
+        same = cnt[0][~band] == o["n_attempt"][~band]
+        assert same.mean() > 0.995, (mode, same.mean())
+
+
+def math_asin(x):
+    import math
+    return math.asin(x)
