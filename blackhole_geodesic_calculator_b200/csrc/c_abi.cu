@@ -41,6 +41,14 @@ int fail(int code, const char* fmt, ...) {
         }                                                                                              \
     } while (0)
 
+// Restores the calling thread's current CUDA device on scope exit: the library selects `device` for its own
+// launches but must not change what the host application (torch, Blender) believes is current.
+struct DeviceRestore {
+    int prev = -1;
+    DeviceRestore() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+    ~DeviceRestore() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 constexpr int kMaxDevices = 64;
 constexpr int kQueueSlots = 256;
 
@@ -266,6 +274,7 @@ int bhg_trace_schwarzschild_f64_ex(const double* in, const double* in_dir, doubl
                                    int32_t* status, int32_t* counters, const int32_t* order, int64_t n,
                                    int32_t layout, const bhg_params* params, const bhg_extras* extras,
                                    int32_t device, void* stream) {
+    DeviceRestore restore_device_on_exit;
     int rc = validate(params, n);
     if (rc) return rc;
     if (layout != BHG_LAYOUT_SOA && layout != BHG_LAYOUT_AOS) return fail(BHG_ERR_INVALID_ARGUMENT, "unknown layout %d", layout);
@@ -289,6 +298,7 @@ int bhg_trace_schwarzschild_f64_host(const double* entry_pos, const double* entr
 int bhg_trace_schwarzschild_f64_host_ex(const double* entry_pos, const double* entry_dir, double* exit_pos,
                                         double* exit_dir, int32_t* status, int32_t* counters, int64_t n,
                                         const bhg_params* params, const bhg_extras* extras, int32_t device) {
+    DeviceRestore restore_device_on_exit;
     int rc = validate(params, n);
     if (rc) return rc;
     if (n > 0 && (!entry_pos || !entry_dir || !exit_pos || !exit_dir || !status))
@@ -341,6 +351,7 @@ int bhg_trace_schwarzschild_f64_host_ex(const double* entry_pos, const double* e
 
 int bhg_generate_rays_f64(const bhg_camera* cam, double r_sphere, int64_t n, double* pos, double* dir, int32_t* hit,
                           int32_t device, void* stream) {
+    DeviceRestore restore_device_on_exit;
     bhg::Camera dc;
     int rc = convert_camera(cam, r_sphere, &dc);
     if (rc) return rc;
@@ -352,6 +363,7 @@ int bhg_generate_rays_f64(const bhg_camera* cam, double r_sphere, int64_t n, dou
 
 int bhg_trace_camera_f64(const bhg_camera* cam, double* exit_pos, double* exit_dir, int32_t* status,
                          int32_t* counters, int64_t n, const bhg_params* params, int32_t device, void* stream) {
+    DeviceRestore restore_device_on_exit;
     int rc = validate(params, n);
     if (rc) return rc;
     bhg::Camera dc;
@@ -374,6 +386,7 @@ int bhg_trace_camera_f64(const bhg_camera* cam, double* exit_pos, double* exit_d
 
 int bhg_trace_camera_f64_host(const bhg_camera* cam, double* exit_pos, double* exit_dir, int32_t* status,
                               int32_t* counters, int64_t n, const bhg_params* params, int32_t device) {
+    DeviceRestore restore_device_on_exit;
     int rc = validate(params, n);
     if (rc) return rc;
     bhg::Camera dc;
@@ -418,6 +431,7 @@ int bhg_trace_camera_f64_host(const bhg_camera* cam, double* exit_pos, double* e
 }
 
 int bhg_sky_uv_f32(const double* exit_dir, const int32_t* status, int64_t n, float* uv, int32_t device, void* stream) {
+    DeviceRestore restore_device_on_exit;
     if (n < 0 || (n > 0 && (!exit_dir || !uv))) return fail(BHG_ERR_INVALID_ARGUMENT, "bad n or NULL buffer");
     DeviceCtx* c;
     int rc = ensure_device(device, &c);
@@ -433,6 +447,7 @@ int bhg_sky_uv_f32(const double* exit_dir, const int32_t* status, int64_t n, flo
 
 int bhg_trace_camera_sky_host(const bhg_camera* cam, float* uv, int32_t* status, int64_t n, const bhg_params* params,
                               int32_t device) {
+    DeviceRestore restore_device_on_exit;
     int rc = validate(params, n);
     if (rc) return rc;
     bhg::Camera dc;
@@ -489,6 +504,7 @@ void bhg_host_free(void* p) {
 
 int bhg_sum_counters(const int32_t* counters_dev, const int32_t* status_dev, int64_t n, int32_t device, void* stream,
                      int64_t* n_attempt, int64_t* n_accept, int64_t* n_integrated) {
+    DeviceRestore restore_device_on_exit;
     DeviceCtx* c;
     int rc = ensure_device(device, &c);
     if (rc) return rc;
@@ -513,6 +529,7 @@ int bhg_sum_counters(const int32_t* counters_dev, const int32_t* status_dev, int
 int64_t bhg_launch_count(void) { return g_launches.load(); }
 
 int bhg_selftest(int32_t device, double* out8) {
+    DeviceRestore restore_device_on_exit;
     DeviceCtx* c;
     int rc = ensure_device(device, &c);
     if (rc) return rc;
@@ -532,6 +549,7 @@ int bhg_selftest(int32_t device, double* out8) {
 }
 
 int bhg_fp64_peak_tflops(int32_t device, double* tflops, double* sm_clock_mhz_est) {
+    DeviceRestore restore_device_on_exit;
     DeviceCtx* c;
     int rc = ensure_device(device, &c);
     if (rc) return rc;
