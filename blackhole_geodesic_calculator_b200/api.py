@@ -45,13 +45,15 @@ def _is_torch(x):
 
 def trace(entry_pos, entry_dir, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, *, max_step=math.inf,
           eps_horizon=0.01, lambda_max=None, mode="parity", refill_threshold=0, image_width=0, device=0,
-          return_counters=False, disk=None):
+          return_counters=False, disk=None, out=None):
     """Integrate N Schwarzschild null geodesics from sphere entry to exit or capture.
 
     entry_pos, entry_dir : [N,3] float64, BH-centred position and coordinate direction (numpy arrays on the
         host, or torch CUDA tensors, which are processed in place on their device and stream).
     image_width : optional scheduling hint — the rays are a row-major image of this width (the reference's
         s -> y -> x order); warps then integrate 8 x 4 pixel tiles.  Never changes results.
+    out : optional (exit_pos, exit_dir, status) numpy arrays to fill (reuse them across frames — ideally
+        `pinned_empty` ones: freshly allocated pageable outputs cost more in page faults than the trace itself).
     disk : optional (r_in, r_out): also return disk_xy[N,2], the first crossing of the equatorial plane z = 0
         with r_in <= r <= r_out (NaN = none) — the in-flight form of the reference's checkHitDisk
         (LimitedRelativisticRenderEngine.py:413-438).  Parity mode only.
@@ -68,9 +70,15 @@ def trace(entry_pos, entry_dir, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, *, m
     if pos.ndim != 2 or pos.shape[1] != 3 or dirs.shape != pos.shape:
         raise ValueError(f"entry_pos and entry_dir must both be [N,3]; got {pos.shape} and {dirs.shape}")
     n = pos.shape[0]
-    exit_pos = np.empty((n, 3), dtype=np.float64)
-    exit_dir = np.empty((n, 3), dtype=np.float64)
-    status = np.empty(n, dtype=np.int32)
+    if out is not None:
+        exit_pos, exit_dir, status = out
+        for a, shp, dt in ((exit_pos, (n, 3), np.float64), (exit_dir, (n, 3), np.float64), (status, (n,), np.int32)):
+            if a.shape != shp or a.dtype != dt or not a.flags.c_contiguous:
+                raise ValueError("out arrays must be C-contiguous exit_pos[N,3] f64, exit_dir[N,3] f64, status[N] i32")
+    else:
+        exit_pos = np.empty((n, 3), dtype=np.float64)
+        exit_dir = np.empty((n, 3), dtype=np.float64)
+        status = np.empty(n, dtype=np.int32)
     counters = np.empty((2, n), dtype=np.int32) if return_counters else None
     p = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
     disk_xy = np.empty((n, 2), dtype=np.float64) if disk is not None else None

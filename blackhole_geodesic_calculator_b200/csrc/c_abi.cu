@@ -8,7 +8,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/bhgeo.h"
@@ -49,6 +52,79 @@ struct DeviceRestore {
     ~DeviceRestore() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// Small persistent pool for host-side copies between pageable user arrays and pinned bounce buffers: one memcpy
+// thread reaches ~10 GB/s, PCIe needs > 50.
+class CopyPool {
+public:
+    static CopyPool& get() {
+        static CopyPool* p = new CopyPool;  // intentionally never destroyed: its threads live until process exit
+        return *p;
+    }
+    void copy(void* dst, const void* src, size_t bytes) {
+        if (bytes < (1u << 20) || workers_.empty()) {
+            memcpy(dst, src, bytes);
+            return;
+        }
+        std::unique_lock<std::mutex> lk(mu_);
+        const size_t parts = workers_.size() + 1;
+        const size_t slice = ((bytes / parts) + 4095) & ~size_t(4095);
+        dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes; slice_ = slice;
+        pending_ = (int)workers_.size();
+        ++generation_;
+        cv_.notify_all();
+        lk.unlock();
+        run_slice(parts - 1);  // the caller takes the last slice
+        lk.lock();
+        done_.wait(lk, [&] { return pending_ == 0; });
+    }
+
+private:
+    CopyPool() {
+        unsigned hc = std::thread::hardware_concurrency();
+        int n = (int)(hc / 2);
+        if (n > 7) n = 7;
+        if (n < 1) n = 1;
+        for (int i = 0; i < n; i++) workers_.emplace_back([this, i] { loop(i); });
+        for (auto& t : workers_) t.detach();  // process-lifetime helpers
+    }
+    void run_slice(size_t i) {
+        const size_t b = i * slice_;
+        if (b >= bytes_) return;
+        const size_t m = (bytes_ - b < slice_) ? bytes_ - b : slice_;
+        memcpy(dst_ + b, src_ + b, m);
+    }
+    void loop(int i) {
+        unsigned long long seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_.wait(lk, [&] { return generation_ != seen; });
+            seen = generation_;
+            lk.unlock();
+            run_slice((size_t)i);
+            lk.lock();
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    std::vector<std::thread> workers_;
+    char* dst_ = nullptr;
+    const char* src_ = nullptr;
+    size_t bytes_ = 0, slice_ = 0;
+    int pending_ = 0;
+    unsigned long long generation_ = 0;
+};
+
+bool is_pageable(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
 constexpr int kMaxDevices = 64;
 constexpr int kQueueSlots = 256;
 
@@ -64,6 +140,10 @@ struct DeviceCtx {
     void* stage = nullptr;
     size_t stage_bytes = 0;
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+    // pinned bounce buffers for pageable user arrays (3 pipeline slots), grow-only
+    void* bounce = nullptr;
+    size_t bounce_bytes = 0;
+    cudaEvent_t slot_in_done[3] = {nullptr, nullptr, nullptr}, slot_out_done[3] = {nullptr, nullptr, nullptr};
     long long* totals = nullptr;  // 3 int64 for bhg_sum_counters
 };
 
@@ -321,29 +401,101 @@ int bhg_trace_schwarzschild_f64_host_ex(const double* entry_pos, const double* e
     int32_t* d_status = (int32_t*)(base + 4 * vec);
     int32_t* d_cnt = d_status + n;  // 2 n
     // chunked pipeline over 3 streams: H2D(i+1) overlaps trace(i) overlaps D2H(i-1)
-    const long long chunk = pick_chunk(n, params->image_width > 0 ? 4LL * params->image_width : 0, 1 << 19);
+    // Pageable user arrays (plain numpy) are staged through pinned bounce slots with a multi-threaded memcpy;
+    // pinned arrays (bhg_host_alloc) are copied directly.
+    const bool bounce = is_pageable(entry_pos) || is_pageable(entry_dir) || is_pageable(exit_pos) ||
+                        is_pageable(exit_dir) || is_pageable(status) || is_pageable(counters) ||
+                        (disk && is_pageable(extras->disk_xy));
+    const long long chunk = pick_chunk(n, params->image_width > 0 ? 4LL * params->image_width : 0, bounce ? 1 << 18 : 1 << 19);
+    // per-slot bounce layout: pos_in | dir_in | pos_out | dir_out | disk | status | counters(2)
+    const size_t slot_bytes = (size_t)chunk * (24 * 4 + 16 + 4 * 3) + 256;
+    char* bb = nullptr;
+    if (bounce) {
+        if (c->bounce_bytes < 3 * slot_bytes) {
+            if (c->bounce) cudaFreeHost(c->bounce);
+            c->bounce = nullptr;
+            c->bounce_bytes = 0;
+            BHG_CUDA(cudaHostAlloc(&c->bounce, 3 * slot_bytes, cudaHostAllocPortable));
+            c->bounce_bytes = 3 * slot_bytes;
+        }
+        for (int i = 0; i < 3; i++) {
+            if (!c->slot_in_done[i]) BHG_CUDA(cudaEventCreateWithFlags(&c->slot_in_done[i], cudaEventDisableTiming));
+            if (!c->slot_out_done[i]) BHG_CUDA(cudaEventCreateWithFlags(&c->slot_out_done[i], cudaEventDisableTiming));
+        }
+        bb = (char*)c->bounce;
+    }
+    CopyPool& pool = CopyPool::get();
+    auto slot_ptrs = [&](int slot, double*& pin, double*& din, double*& pout, double*& dout, double*& dsk,
+                         int32_t*& st, int32_t*& cn) {
+        char* sb = bb + (size_t)slot * slot_bytes;
+        pin = (double*)sb;
+        din = pin + 3 * chunk;
+        pout = din + 3 * chunk;
+        dout = pout + 3 * chunk;
+        dsk = dout + 3 * chunk;
+        st = (int32_t*)(dsk + 2 * chunk);
+        cn = st + chunk;
+    };
+    // copies a finished chunk from its bounce slot to the user's arrays
+    auto drain = [&](long long b, int slot) -> int {
+        const long long m = (n - b < chunk) ? (n - b) : chunk;
+        double *pin, *din, *pout, *dout, *dsk;
+        int32_t *st, *cn;
+        slot_ptrs(slot, pin, din, pout, dout, dsk, st, cn);
+        BHG_CUDA(cudaEventSynchronize(c->slot_out_done[slot]));
+        pool.copy(exit_pos + 3 * b, pout, (size_t)m * 24);
+        pool.copy(exit_dir + 3 * b, dout, (size_t)m * 24);
+        memcpy(status + b, st, (size_t)m * 4);
+        if (counters) {
+            memcpy(counters + b, cn, (size_t)m * 4);
+            memcpy(counters + n + b, cn + m, (size_t)m * 4);
+        }
+        if (disk) memcpy(extras->disk_xy + 2 * b, dsk, (size_t)m * 16);
+        return 0;
+    };
     int si = 0;
-    for (long long b = 0; b < n; b += chunk, si = (si + 1) % 3) {
+    long long idx = 0;
+    for (long long b = 0; b < n; b += chunk, si = (si + 1) % 3, idx++) {
         const long long m = (n - b < chunk) ? (n - b) : chunk;
         cudaStream_t s = c->streams[si];
-        BHG_CUDA(cudaMemcpyAsync(d_pin + 3 * b, entry_pos + 3 * b, (size_t)m * 24, cudaMemcpyHostToDevice, s));
-        BHG_CUDA(cudaMemcpyAsync(d_din + 3 * b, entry_dir + 3 * b, (size_t)m * 24, cudaMemcpyHostToDevice, s));
         // counters of a chunk live at [b, b+m) and [n + b, ...): give the kernel a chunk-local view by
         // writing attempts/accepted into a 2m block and scattering on the way back
         int32_t* cnt_chunk = counters ? d_cnt + 2 * b : nullptr;
         bhg_extras ex_chunk;
         if (disk) { ex_chunk = *extras; ex_chunk.disk_xy = d_disk + 2 * b; }
+        double *pin = nullptr, *din = nullptr, *pout = nullptr, *dout = nullptr, *dsk = nullptr;
+        int32_t *st = nullptr, *cn = nullptr;
+        if (bounce) {
+            // slot si was last used by chunk idx-3, whose results were drained at iteration idx-1
+            if (idx >= 3) BHG_CUDA(cudaEventSynchronize(c->slot_in_done[si]));
+            slot_ptrs(si, pin, din, pout, dout, dsk, st, cn);
+            pool.copy(pin, entry_pos + 3 * b, (size_t)m * 24);
+            pool.copy(din, entry_dir + 3 * b, (size_t)m * 24);
+        }
+        BHG_CUDA(cudaMemcpyAsync(d_pin + 3 * b, bounce ? pin : entry_pos + 3 * b, (size_t)m * 24, cudaMemcpyHostToDevice, s));
+        BHG_CUDA(cudaMemcpyAsync(d_din + 3 * b, bounce ? din : entry_dir + 3 * b, (size_t)m * 24, cudaMemcpyHostToDevice, s));
+        if (bounce) BHG_CUDA(cudaEventRecord(c->slot_in_done[si], s));
         rc = launch_trace(*c, d_pin + 3 * b, d_din + 3 * b, d_pout + 3 * b, d_dout + 3 * b, d_status + b, cnt_chunk,
                           nullptr, m, bhg::IN_AOS, params->image_width, params, s, disk ? &ex_chunk : nullptr);
         if (rc) return rc;
-        if (disk) BHG_CUDA(cudaMemcpyAsync(extras->disk_xy + 2 * b, d_disk + 2 * b, (size_t)m * 16, cudaMemcpyDeviceToHost, s));
-        BHG_CUDA(cudaMemcpyAsync(exit_pos + 3 * b, d_pout + 3 * b, (size_t)m * 24, cudaMemcpyDeviceToHost, s));
-        BHG_CUDA(cudaMemcpyAsync(exit_dir + 3 * b, d_dout + 3 * b, (size_t)m * 24, cudaMemcpyDeviceToHost, s));
-        BHG_CUDA(cudaMemcpyAsync(status + b, d_status + b, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+        if (disk) BHG_CUDA(cudaMemcpyAsync(bounce ? dsk : extras->disk_xy + 2 * b, d_disk + 2 * b, (size_t)m * 16, cudaMemcpyDeviceToHost, s));
+        BHG_CUDA(cudaMemcpyAsync(bounce ? pout : exit_pos + 3 * b, d_pout + 3 * b, (size_t)m * 24, cudaMemcpyDeviceToHost, s));
+        BHG_CUDA(cudaMemcpyAsync(bounce ? dout : exit_dir + 3 * b, d_dout + 3 * b, (size_t)m * 24, cudaMemcpyDeviceToHost, s));
+        BHG_CUDA(cudaMemcpyAsync(bounce ? st : status + b, d_status + b, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
         if (counters) {
-            BHG_CUDA(cudaMemcpyAsync(counters + b, cnt_chunk, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
-            BHG_CUDA(cudaMemcpyAsync(counters + n + b, cnt_chunk + m, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+            BHG_CUDA(cudaMemcpyAsync(bounce ? cn : counters + b, cnt_chunk, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+            BHG_CUDA(cudaMemcpyAsync(bounce ? cn + m : counters + n + b, cnt_chunk + m, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
         }
+        if (bounce) {
+            BHG_CUDA(cudaEventRecord(c->slot_out_done[si], s));
+            // drain the chunk issued two iterations ago while the GPU works on the last two
+            if (idx >= 2 && (rc = drain(b - 2 * chunk, (si + 1) % 3))) return rc;
+        }
+    }
+    if (bounce) {
+        const long long nchunks = idx;
+        for (long long j = (nchunks >= 2 ? nchunks - 2 : 0); j < nchunks; j++)
+            if ((rc = drain(j * chunk, (int)(j % 3)))) return rc;
     }
     for (auto& s : c->streams) BHG_CUDA(cudaStreamSynchronize(s));
     return 0;

@@ -12,3 +12,7 @@ def wall(fn, reps=3):
 print("pageable numpy in/out (api.trace allocates outputs): %.1f ms" % wall(lambda: api.trace(pos, d, image_width=1024)))
 ppos, pd = api.pinned_empty((n, 3)), api.pinned_empty((n, 3)); ppos[:] = pos; pd[:] = d
 print("pinned inputs, pageable outputs: %.1f ms" % wall(lambda: api.trace(ppos, pd, image_width=1024)))
+outs = (np.empty((n, 3)), np.empty((n, 3)), np.empty(n, np.int32))
+print("pageable inputs, reused pageable outputs (out=): %.1f ms" % wall(lambda: api.trace(pos, d, image_width=1024, out=outs)))
+pouts = (api.pinned_empty((n, 3)), api.pinned_empty((n, 3)), api.pinned_empty((n,), np.int32))
+print("all pinned (out=): %.1f ms" % wall(lambda: api.trace(ppos, pd, image_width=1024, out=pouts)))
