@@ -395,8 +395,7 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
             if (h_abs < min_step) {
                 state = STEP_FAILED;  // TOO_SMALL_STEP; (k, x) hold the last accepted state
             } else {
-                double t_new = t + h_abs;
-                if (t_new - t_bound > 0.0) t_new = t_bound;
+                const double t_new = fmin(t + h_abs, t_bound);  // clip to t_bound (rk.py:139-140)
                 const double h = t_new - t;
                 h_abs = fabs(h);
                 n_attempt++;
@@ -405,11 +404,11 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
                 if (en2 < 1.0) {
                     n_accept++;
                     const double factor = step_factor_accept(en2, rejected ? 1.0 : 10.0);
-                    // events on the accepted step (ivp.py:134-158): horizon either direction, sphere upward
-                    const double gh0 = x[IR] - a.r_hor, gh1 = xn[IR] - a.r_hor;
-                    const double ge0 = x[IR] - a.r_sphere, ge1 = xn[IR] - a.r_sphere;
-                    const bool act_h = (gh0 <= 0.0 && gh1 >= 0.0) || (gh0 >= 0.0 && gh1 <= 0.0);
-                    const bool act_e = a.has_outer && (ge0 <= 0.0 && ge1 >= 0.0);
+                    // events on the accepted step (ivp.py:134-158).  Horizon (direction 0): a running ray always has
+                    // r > r_hor (it starts there and stops at its first crossing), so "g0 >= 0 and g1 <= 0" is just
+                    // r_new <= r_hor and the upward branch cannot occur.  Sphere (direction +1): g0 <= 0 and g1 >= 0.
+                    const bool act_h = xn[IR] <= a.r_hor;
+                    const bool act_e = a.has_outer && (x[IR] <= a.r_sphere) && (xn[IR] >= a.r_sphere);
                     if (act_h || act_e) {
                         state = act_h ? (act_e ? PEND_HE : PEND_H) : PEND_E;
                         h_abs = h;  // keep the step length for the dense output
@@ -435,7 +434,7 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
                             x[i] = xn[i];
                             K[0][i] = K[6][i];  // FSAL
                         }
-                        if (t - t_bound >= 0.0) state = LAMBDA_EXHAUSTED;
+                        if (t >= t_bound) state = LAMBDA_EXHAUSTED;
                     }
                 } else {
                     h_abs *= step_factor_reject(en2);
