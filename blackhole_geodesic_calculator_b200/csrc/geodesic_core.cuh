@@ -48,6 +48,19 @@ enum LaneState : int {
 // small FP64 building blocks
 // ---------------------------------------------------------------------------------------------
 
+// Comparisons of NON-NEGATIVE doubles on the integer pipe: for such values the order of the numbers is the order
+// of their bit patterns.  The unsigned compare sends a NaN of either sign (and any negative value) to "huge",
+// i.e. lt_nn(NaN, x) is false like the IEEE compare.  (Every FP64-pipe instruction saved is ~0.16 % of the
+// kernel: profiles/r1m_experiments.txt.)
+__device__ __forceinline__ bool lt_nn(double a, double b) {
+    return (unsigned long long)__double_as_longlong(a) < (unsigned long long)__double_as_longlong(b);
+}
+__device__ __forceinline__ bool le_nn(double a, double b) {
+    return (unsigned long long)__double_as_longlong(a) <= (unsigned long long)__double_as_longlong(b);
+}
+__device__ __forceinline__ double min_nn(double a, double b) { return lt_nn(b, a) ? b : a; }  // NaN a -> b
+__device__ __forceinline__ double max_nn(double a, double b) { return lt_nn(a, b) ? b : a; }
+
 // 1/a for normal, finite a (call sites guarantee that, or produce NaN/inf that the step controller
 // rejects): MUFU.RCP64H seed, one third-order and one second-order refinement (5 DFMA).  Measured on
 // B200 against IEEE division: bit-identical on the self-test sweep (profiles/r1b_selftest.txt).
@@ -97,7 +110,7 @@ __device__ __forceinline__ double inv_tenth_root(double a) {
     double res = fma(x, p, x);
     // seed worse than 1e-5 (never with the MUFU seed) or NaN: cold library fallback.  Tested after the result is
     // formed so that the compare overlaps the polynomial instead of sitting on the serial path.
-    if (!(fabs(d) < 1e-4)) res = pow_cold(a, -0.1);
+    if (!lt_nn(fabs(d), 1e-4)) res = pow_cold(a, -0.1);
     return res;
 }
 
@@ -327,19 +340,19 @@ __device__ __forceinline__ double rk45_attempt(const double (&k)[NK], const doub
         e = fma(TAB(E4), K[3][i], e);
         e = fma(TAB(E5), K[4][i], e);
         e = fma(TAB(E6), K[5][i], e);
-        ek[i] = fma(TAB(E7), K[6][i], e) * h;
+        ek[i] = fma(TAB(E7), K[6][i], e);          // error / h   (momentum half)
         double g = TAB(EA1) * K[0][i];
         g = fma(TAB(EA2), K[1][i], g);
         g = fma(TAB(EA3), K[2][i], g);
         g = fma(TAB(EA4), K[3][i], g);
         g = fma(TAB(EA5), K[4][i], g);
-        ex[i] = fma(TAB(EA6), K[5][i], g) * h2;
+        ex[i] = fma(TAB(EA6), K[5][i], g);         // error / h^2 (position half)
         sk[i] = fma(abs_max(k[i], kn[i]), rtol, atol);
         sx[i] = fma(abs_max(x[i], xn[i]), rtol, atol);
     }
     // one reciprocal per group of four scales (two momentum/position pairs); scales are >= atol so the
-    // products neither overflow nor underflow
-    double esum = 0.0, esum1 = 0.0;  // two independent accumulation chains
+    // products neither overflow nor underflow.  sum (e_i/scale_i)^2 = h^2 (S_k + h^2 S_x): h is applied once.
+    double sumk = 0.0, sumx = 0.0;
 #pragma unroll
     for (int i = 0; i + 1 < NK; i += 2) {
         const double pa = sk[i] * sx[i], pb = sk[i + 1] * sx[i + 1];
@@ -347,19 +360,19 @@ __device__ __forceinline__ double rk45_attempt(const double (&k)[NK], const doub
         const double ia = inv * pb, ib = inv * pa;  // 1/pa, 1/pb
         const double q0 = ek[i] * (ia * sx[i]), q1 = ex[i] * (ia * sk[i]);
         const double q2 = ek[i + 1] * (ib * sx[i + 1]), q3 = ex[i + 1] * (ib * sk[i + 1]);
-        esum = fma(q0, q0, esum);
-        esum1 = fma(q2, q2, esum1);
-        esum = fma(q1, q1, esum);
-        esum1 = fma(q3, q3, esum1);
+        sumk = fma(q0, q0, sumk);
+        sumx = fma(q1, q1, sumx);
+        sumk = fma(q2, q2, sumk);
+        sumx = fma(q3, q3, sumx);
     }
-    esum += esum1;
     if (NK & 1) {
         constexpr int i = NK - 1;
         const double inv = fast_rcp(sk[i] * sx[i]);
         const double q0 = ek[i] * (inv * sx[i]), q1 = ex[i] * (inv * sk[i]);
-        esum = fma(q0, q0, esum);
-        esum = fma(q1, q1, esum);
+        sumk = fma(q0, q0, sumk);
+        sumx = fma(q1, q1, sumx);
     }
+    const double esum = h2 * fma(h2, sumx, sumk);
     return esum;
 }
 
@@ -367,11 +380,11 @@ __device__ __forceinline__ double rk45_attempt(const double (&k)[NK], const doub
 // caller already knows whether the step was accepted (en2 < 1) or rejected (en2 >= 1 or NaN).
 //   accepted: min(hi, 0.9 err^-0.2), hi = 10 (or 1 after a rejection); en2 -> 0 gives hi (0.9 (1e-12)^-0.1 = 14.3)
 __device__ __forceinline__ double step_factor_accept(double en2, double hi) {
-    return fmin(hi, 0.9 * inv_tenth_root(fmax(en2, 1e-12)));
+    return min_nn(0.9 * inv_tenth_root(max_nn(en2, 1e-12)), hi);
 }
 //   rejected: max(0.2, 0.9 err^-0.2); huge / inf / NaN error norms give 0.2 (fmin drops the NaN; 0.9 (1e8)^-0.1 = 0.14)
 __device__ __forceinline__ double step_factor_reject(double en2) {
-    return fmax(0.2, 0.9 * inv_tenth_root(fmin(en2, 1e8)));
+    return max_nn(0.9 * inv_tenth_root(min_nn(en2, 1e8)), 0.2);
 }
 
 // 10 * |nextafter(t, +inf) - t|  for t >= 0 (scipy/_ivp/rk.py:119)

@@ -389,26 +389,26 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
             // ---------------- one RK45 attempt (rk.py:111-176) ----------------
             const double min_step = min_step_at(t);
             if (!rejected) {
-                if (h_abs > a.max_step) h_abs = a.max_step;
-                else if (h_abs < min_step) h_abs = min_step;
+                if (lt_nn(a.max_step, h_abs)) h_abs = a.max_step;
+                else if (lt_nn(h_abs, min_step)) h_abs = min_step;
             }
-            if (h_abs < min_step) {
+            if (lt_nn(h_abs, min_step)) {
                 state = STEP_FAILED;  // TOO_SMALL_STEP; (k, x) hold the last accepted state
             } else {
-                const double t_new = fmin(t + h_abs, t_bound);  // clip to t_bound (rk.py:139-140)
+                const double t_new = min_nn(t + h_abs, t_bound);  // clip to t_bound (rk.py:139-140)
                 const double h = t_new - t;
                 h_abs = fabs(h);
                 n_attempt++;
                 const double esum = rk45_attempt<NK>(k, x, K, kn, xn, h, a.rs, a.rtol, a.atol);
                 const double en2 = esum * (1.0 / (2 * NK));  // (RMS error norm)^2 over all 2 NK components
-                if (en2 < 1.0) {
+                if (lt_nn(en2, 1.0)) {
                     n_accept++;
                     const double factor = step_factor_accept(en2, rejected ? 1.0 : 10.0);
                     // events on the accepted step (ivp.py:134-158).  Horizon (direction 0): a running ray always has
                     // r > r_hor (it starts there and stops at its first crossing), so "g0 >= 0 and g1 <= 0" is just
                     // r_new <= r_hor and the upward branch cannot occur.  Sphere (direction +1): g0 <= 0 and g1 >= 0.
                     const bool act_h = xn[IR] <= a.r_hor;
-                    const bool act_e = a.has_outer && (x[IR] <= a.r_sphere) && (xn[IR] >= a.r_sphere);
+                    const bool act_e = a.has_outer && le_nn(x[IR], a.r_sphere) && le_nn(a.r_sphere, xn[IR]);
                     if (act_h || act_e) {
                         state = act_h ? (act_e ? PEND_HE : PEND_H) : PEND_E;
                         h_abs = h;  // keep the step length for the dense output
@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
                             x[i] = xn[i];
                             K[0][i] = K[6][i];  // FSAL
                         }
-                        if (t >= t_bound) state = LAMBDA_EXHAUSTED;
+                        if (le_nn(t_bound, t)) state = LAMBDA_EXHAUSTED;
                     }
                 } else {
                     h_abs *= step_factor_reject(en2);
