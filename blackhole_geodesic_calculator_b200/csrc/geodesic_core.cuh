@@ -58,6 +58,12 @@ __device__ __forceinline__ bool lt_nn(double a, double b) {
 __device__ __forceinline__ bool le_nn(double a, double b) {
     return (unsigned long long)__double_as_longlong(a) <= (unsigned long long)__double_as_longlong(b);
 }
+// |a| < c for c > 0, on the integer pipe (written on the 32-bit halves so it is not folded back into an FP64 |x|)
+__device__ __forceinline__ bool abs_lt(double a, double c) {
+    const unsigned long long v = ((unsigned long long)(unsigned)(__double2hiint(a) & 0x7fffffff) << 32) |
+                                 (unsigned)__double2loint(a);
+    return v < (unsigned long long)__double_as_longlong(c);
+}
 __device__ __forceinline__ double min_nn(double a, double b) { return lt_nn(b, a) ? b : a; }  // NaN a -> b
 __device__ __forceinline__ double max_nn(double a, double b) { return lt_nn(a, b) ? b : a; }
 
@@ -110,7 +116,7 @@ __device__ __forceinline__ double inv_tenth_root(double a) {
     double res = fma(x, p, x);
     // seed worse than 1e-5 (never with the MUFU seed) or NaN: cold library fallback.  Tested after the result is
     // formed so that the compare overlaps the polynomial instead of sitting on the serial path.
-    if (!lt_nn(fabs(d), 1e-4)) res = pow_cold(a, -0.1);
+    if (!abs_lt(d, 1e-4)) res = pow_cold(a, -0.1);
     return res;
 }
 
@@ -262,50 +268,50 @@ __device__ __forceinline__ double rk45_attempt(const double (&k)[NK], const doub
                                                double (&kn)[NK], double (&xn)[NK], const double h, const double rs,
                                                const double rtol, const double atol) {
     const double h2 = h * h;
-    double kt[NK], xt[NK];
+    double kt[NK], xt[NK], hk[NK];
 #pragma unroll
-    for (int i = 0; i < NK; i++) xt[i] = x[i];
+    for (int i = 0; i < NK; i++) {
+        xt[i] = x[i];
+        hk[i] = Rhs<NK>::needs_x(i) ? h * k[i] : 0.0;  // h k for the position stage values (r, theta only)
+    }
     // ---- stage 2
     {
-        const double ha = h * TAB(A21), hc = h * TAB(C2);
+        const double ha = h * TAB(A21);
 #pragma unroll
         for (int i = 0; i < NK; i++) {
             kt[i] = fma(ha, K[0][i], k[i]);
-            if (Rhs<NK>::needs_x(i)) xt[i] = fma(hc, k[i], x[i]);
+            if (Rhs<NK>::needs_x(i)) xt[i] = fma(TAB(C2), hk[i], x[i]);
         }
         Rhs<NK>::eval(kt, xt, rs, K[1]);
     }
     // ---- stage 3
     {
-        const double hc = h * TAB(C3);
 #pragma unroll
         for (int i = 0; i < NK; i++) {
             kt[i] = fma(h, fma(TAB(A32), K[1][i], TAB(A31) * K[0][i]), k[i]);
-            if (Rhs<NK>::needs_x(i)) xt[i] = fma(h2, TAB(AA31) * K[0][i], fma(hc, k[i], x[i]));
+            if (Rhs<NK>::needs_x(i)) xt[i] = fma(h2, TAB(AA31) * K[0][i], fma(TAB(C3), hk[i], x[i]));
         }
         Rhs<NK>::eval(kt, xt, rs, K[2]);
     }
     // ---- stage 4
     {
-        const double hc = h * TAB(C4);
 #pragma unroll
         for (int i = 0; i < NK; i++) {
             kt[i] = fma(h, fma(TAB(A43), K[2][i], fma(TAB(A42), K[1][i], TAB(A41) * K[0][i])), k[i]);
             if (Rhs<NK>::needs_x(i))
-                xt[i] = fma(h2, fma(TAB(AA42), K[1][i], TAB(AA41) * K[0][i]), fma(hc, k[i], x[i]));
+                xt[i] = fma(h2, fma(TAB(AA42), K[1][i], TAB(AA41) * K[0][i]), fma(TAB(C4), hk[i], x[i]));
         }
         Rhs<NK>::eval(kt, xt, rs, K[3]);
     }
     // ---- stage 5
     {
-        const double hc = h * TAB(C5);
 #pragma unroll
         for (int i = 0; i < NK; i++) {
             kt[i] = fma(h, fma(TAB(A54), K[3][i], fma(TAB(A53), K[2][i], fma(TAB(A52), K[1][i], TAB(A51) * K[0][i]))),
                         k[i]);
             if (Rhs<NK>::needs_x(i))
                 xt[i] = fma(h2, fma(TAB(AA53), K[2][i], fma(TAB(AA52), K[1][i], TAB(AA51) * K[0][i])),
-                            fma(hc, k[i], x[i]));
+                            fma(TAB(C5), hk[i], x[i]));
         }
         Rhs<NK>::eval(kt, xt, rs, K[4]);
     }
@@ -320,7 +326,7 @@ __device__ __forceinline__ double rk45_attempt(const double (&k)[NK], const doub
             if (Rhs<NK>::needs_x(i))
                 xt[i] = fma(h2,
                             fma(TAB(AA64), K[3][i], fma(TAB(AA63), K[2][i], fma(TAB(AA62), K[1][i], TAB(AA61) * K[0][i]))),
-                            fma(h, k[i], x[i]));
+                            x[i] + hk[i]);
         }
         Rhs<NK>::eval(kt, xt, rs, K[5]);
     }

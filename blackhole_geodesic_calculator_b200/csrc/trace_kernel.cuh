@@ -396,8 +396,8 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
                 state = STEP_FAILED;  // TOO_SMALL_STEP; (k, x) hold the last accepted state
             } else {
                 const double t_new = min_nn(t + h_abs, t_bound);  // clip to t_bound (rk.py:139-140)
-                const double h = t_new - t;
-                h_abs = fabs(h);
+                const double h = t_new - t;  // >= 0: integration runs forward in lambda
+                h_abs = h;
                 n_attempt++;
                 const double esum = rk45_attempt<NK>(k, x, K, kn, xn, h, a.rs, a.rtol, a.atol);
                 const double en2 = esum * (1.0 / (2 * NK));  // (RMS error norm)^2 over all 2 NK components
