@@ -382,15 +382,21 @@ __device__ __forceinline__ double rk45_attempt(const double (&k)[NK], const doub
     return esum;
 }
 
-// step-size factors 0.9 * err^(-1/5), with err^2 = en2 (scipy/_ivp/rk.py:148-163).  Branch-free clamps: the
-// caller already knows whether the step was accepted (en2 < 1) or rejected (en2 >= 1 or NaN).
-//   accepted: min(hi, 0.9 err^-0.2), hi = 10 (or 1 after a rejection); en2 -> 0 gives hi (0.9 (1e-12)^-0.1 = 14.3)
-__device__ __forceinline__ double step_factor_accept(double en2, double hi) {
-    return min_nn(0.9 * inv_tenth_root(max_nn(en2, 1e-12)), hi);
+// step-size factors 0.9 * err^(-1/5) (scipy/_ivp/rk.py:148-163) as a function of the SUM of squares
+// esum = n * err^2 (n = 2 NK components): 0.9 (esum/n)^(-1/10) = (0.9 n^(1/10)) esum^(-1/10), so the division by
+// n costs nothing.  Branch-free clamps: the caller already knows whether the step was accepted (esum < n) or
+// rejected (esum >= n or NaN).
+//   accepted: min(hi, f), hi = 10 (or 1 after a rejection); esum -> 0 gives hi (f(1e-11) > 11)
+template <int N2>
+__device__ __forceinline__ double step_factor_accept(double esum, double hi) {
+    constexpr double c = (N2 == 8) ? 0.9 * 1.2311444133449163 : 0.9 * 1.1962311988513155;  // 0.9 * N2^(1/10)
+    return min_nn(c * inv_tenth_root(max_nn(esum, 1e-11)), hi);
 }
-//   rejected: max(0.2, 0.9 err^-0.2); huge / inf / NaN error norms give 0.2 (fmin drops the NaN; 0.9 (1e8)^-0.1 = 0.14)
-__device__ __forceinline__ double step_factor_reject(double en2) {
-    return max_nn(0.9 * inv_tenth_root(min_nn(en2, 1e8)), 0.2);
+//   rejected: max(0.2, f); huge / inf / NaN error norms give 0.2 (min_nn drops the NaN; f(1e9) = 0.14)
+template <int N2>
+__device__ __forceinline__ double step_factor_reject(double esum) {
+    constexpr double c = (N2 == 8) ? 0.9 * 1.2311444133449163 : 0.9 * 1.1962311988513155;
+    return max_nn(c * inv_tenth_root(min_nn(esum, 1e9)), 0.2);
 }
 
 // 10 * |nextafter(t, +inf) - t|  for t >= 0 (scipy/_ivp/rk.py:119)

@@ -387,12 +387,15 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
 
         if (state == LANE_RUNNING) {
             // ---------------- one RK45 attempt (rk.py:111-176) ----------------
-            const double min_step = min_step_at(t);
-            if (!rejected) {
-                if (lt_nn(a.max_step, h_abs)) h_abs = a.max_step;
-                else if (lt_nn(h_abs, min_step)) h_abs = min_step;
+            // min_step = 10 ulp(t) <= 2.3e-15 t: the exact value is only formed when h_abs is that small
+            bool too_small = false;
+            if (!rejected && lt_nn(a.max_step, h_abs)) h_abs = a.max_step;
+            if (lt_nn(h_abs, t * 2.3e-15)) {
+                const double min_step = min_step_at(t);
+                if (!rejected && lt_nn(h_abs, min_step)) h_abs = min_step;
+                too_small = lt_nn(h_abs, min_step);
             }
-            if (lt_nn(h_abs, min_step)) {
+            if (too_small) {
                 state = STEP_FAILED;  // TOO_SMALL_STEP; (k, x) hold the last accepted state
             } else {
                 const double t_new = min_nn(t + h_abs, t_bound);  // clip to t_bound (rk.py:139-140)
@@ -400,10 +403,10 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
                 h_abs = h;
                 n_attempt++;
                 const double esum = rk45_attempt<NK>(k, x, K, kn, xn, h, a.rs, a.rtol, a.atol);
-                const double en2 = esum * (1.0 / (2 * NK));  // (RMS error norm)^2 over all 2 NK components
-                if (lt_nn(en2, 1.0)) {
+                // esum = 2 NK (RMS error norm)^2: accepted iff error norm < 1 (rk.py:148)
+                if (lt_nn(esum, 2.0 * NK)) {
                     n_accept++;
-                    const double factor = step_factor_accept(en2, rejected ? 1.0 : 10.0);
+                    const double factor = step_factor_accept<2 * NK>(esum, rejected ? 1.0 : 10.0);
                     // events on the accepted step (ivp.py:134-158).  Horizon (direction 0): a running ray always has
                     // r > r_hor (it starts there and stops at its first crossing), so "g0 >= 0 and g1 <= 0" is just
                     // r_new <= r_hor and the upward branch cannot occur.  Sphere (direction +1): g0 <= 0 and g1 >= 0.
@@ -437,7 +440,7 @@ __global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceA
                         if (le_nn(t_bound, t)) state = LAMBDA_EXHAUSTED;
                     }
                 } else {
-                    h_abs *= step_factor_reject(en2);
+                    h_abs *= step_factor_reject<2 * NK>(esum);
                     rejected = true;
                 }
             }
