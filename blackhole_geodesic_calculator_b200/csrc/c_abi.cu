@@ -151,7 +151,7 @@ DeviceCtx g_ctx[kMaxDevices];
 
 template <int NK, int IN>
 int query_occupancy(int* out) {
-    BHG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, bhg::trace_kernel<NK, IN>, 128, 0));
+    BHG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, bhg::trace_kernel<NK, IN>, BHG_BLOCK, 0));
     return 0;
 }
 
@@ -265,17 +265,17 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
     a.queue_head = c.queue_slots + slot;
     BHG_CUDA(cudaMemsetAsync(a.queue_head, 0, sizeof(unsigned long long), stream));
     const int mode = p->mode;
-    long long want_blocks = (n + 127) / 128;
+    long long want_blocks = (n + BHG_BLOCK - 1) / BHG_BLOCK;
     long long max_blocks = (long long)c.sm_count * c.blocks_per_sm[mode][in_kind];
     int blocks = (int)(want_blocks < max_blocks ? want_blocks : max_blocks);
     if (disk) {
-        bhg::trace_kernel<4, bhg::IN_AOS, true><<<blocks, 128, 0, stream>>>(a);
+        bhg::trace_kernel<4, bhg::IN_AOS, true><<<blocks, BHG_BLOCK, 0, stream>>>(a);
     } else if (mode == BHG_MODE_PARITY) {
-        if (in_kind == bhg::IN_AOS) bhg::trace_kernel<4, bhg::IN_AOS><<<blocks, 128, 0, stream>>>(a);
-        else bhg::trace_kernel<4, bhg::IN_SOA><<<blocks, 128, 0, stream>>>(a);
+        if (in_kind == bhg::IN_AOS) bhg::trace_kernel<4, bhg::IN_AOS><<<blocks, BHG_BLOCK, 0, stream>>>(a);
+        else bhg::trace_kernel<4, bhg::IN_SOA><<<blocks, BHG_BLOCK, 0, stream>>>(a);
     } else {
-        if (in_kind == bhg::IN_AOS) bhg::trace_kernel<3, bhg::IN_AOS><<<blocks, 128, 0, stream>>>(a);
-        else bhg::trace_kernel<3, bhg::IN_SOA><<<blocks, 128, 0, stream>>>(a);
+        if (in_kind == bhg::IN_AOS) bhg::trace_kernel<3, bhg::IN_AOS><<<blocks, BHG_BLOCK, 0, stream>>>(a);
+        else bhg::trace_kernel<3, bhg::IN_SOA><<<blocks, BHG_BLOCK, 0, stream>>>(a);
     }
     g_launches.fetch_add(1);
     BHG_CUDA(cudaGetLastError());

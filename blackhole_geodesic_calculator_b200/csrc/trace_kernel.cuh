@@ -253,12 +253,17 @@ __device__ __forceinline__ bool disk_crossing(const TraceArgs& a, long long idx,
     return true;
 }
 
+// One 512-thread block per SM (16 warps, 128 registers/thread).  Measured on B200 with the same 16 warps/SM:
+// 32x16: 3.514, 64x8: 3.517, 128x4: 3.517, 256x2: 3.493, 512x1: 3.458 ms/frame (profiles/r1m_experiments.txt).
 #ifndef BHG_MIN_BLOCKS
-#define BHG_MIN_BLOCKS 4
+#define BHG_MIN_BLOCKS 1
+#endif
+#ifndef BHG_BLOCK
+#define BHG_BLOCK 512
 #endif
 
 template <int NK, int IN, bool DISK = false>
-__global__ void __launch_bounds__(128, BHG_MIN_BLOCKS) trace_kernel(const TraceArgs a) {
+__global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const TraceArgs a) {
     static_assert(!DISK || NK == 4, "the disk event is defined for the spherical (parity) state");
     constexpr int IR = 1;  // index of r in x
     constexpr unsigned FULL = 0xffffffffu;
