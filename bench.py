@@ -292,10 +292,25 @@ def run_b200(args):
     torch.cuda.synchronize(dev)
     cam_times.append(time.perf_counter() - t0)
 
+    # (d) the same host-buffer contract with float32 arrays (Blender's native precision): 28 B/ray over PCIe
+    f_pos, f_dir = api.pinned_empty((n, 3), np.float32), api.pinned_empty((n, 3), np.float32)
+    f_pos[:] = pos_h
+    f_dir[:] = dir_h
+    f_out = (api.pinned_empty((n, 3), np.float32), api.pinned_empty((n, 3), np.float32), pin_st)
+    kw32 = dict(mode=args.mode, refill_threshold=args.threshold, image_width=0 if args.no_tiles else W, device=local,
+                out=f_out)
+    api.trace_f32(f_pos, f_dir, **kw32)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        api.trace_f32(f_pos, f_dir, **kw32)
+    torch.cuda.synchronize(dev)
+    cam_times.append(time.perf_counter() - t0)
+
     t = torch.tensor([total_ms, e2e_s * 1e3] + [c * 1e3 for c in cam_times], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, cam_full_ms, cam_dir_ms, cam_uv_ms = (float(v) for v in t)
+    total_ms, e2e_ms, cam_full_ms, cam_dir_ms, cam_uv_ms, f32_ms = (float(v) for v in t)
     value = world * n * args.steps / (total_ms * 1e-3)
     e2e_value = world * n * e2e_steps / (e2e_ms * 1e-3)
 
@@ -342,6 +357,10 @@ def run_b200(args):
                                                  "h2d_bytes_per_step": 176, "d2h_bytes_per_step": n * 12},
                            "api": "bhg_trace_camera_f64_host / bhg_trace_camera_sky_host: rays generated on the device from the camera struct "
                                   "(next-row 1), pinned numpy outputs"},
+            "e2e_f32io": {"value": world * n * e2e_steps / (f32_ms * 1e-3), "unit": "rays/s",
+                          "h2d_bytes_per_step": n * 24, "d2h_bytes_per_step": n * 28,
+                          "api": "bhg_trace_schwarzschild_f32io_host: float32 [N,3] host arrays in/out (Blender's native "
+                                 "precision), FP64 integration"},
             "gpu_launches": int(launches),
             "kernel_ms": {"mean": kavg, "min": float(np.min(kern_ms)), "max": float(np.max(kern_ms))},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak, "unit": "TFLOP/s",

@@ -71,6 +71,10 @@ _SIGNATURES = {
     "bhg_trace_schwarzschild_f64_host_ex": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, ctypes.c_int64,
                                                            ctypes.POINTER(BhgParams), ctypes.POINTER(BhgExtras),
                                                            ctypes.c_int32]),
+    "bhg_trace_schwarzschild_f32io": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, ctypes.c_int64,
+                                                     ctypes.POINTER(BhgParams), ctypes.c_int32, _P]),
+    "bhg_trace_schwarzschild_f32io_host": (ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.c_int64,
+                                                          ctypes.POINTER(BhgParams), ctypes.c_int32]),
     "bhg_generate_rays_f64": (ctypes.c_int, [ctypes.POINTER(BhgCamera), ctypes.c_double, ctypes.c_int64, _P, _P, _P,
                                              ctypes.c_int32, _P]),
     "bhg_trace_camera_f64": (ctypes.c_int, [ctypes.POINTER(BhgCamera), _P, _P, _P, _P, ctypes.c_int64,

@@ -209,6 +209,29 @@ def trace_camera(cam: BhgCamera, n, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, 
     return ep, ed, st
 
 
+def trace_f32(entry_pos, entry_dir, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, *, max_step=math.inf,
+              eps_horizon=0.01, lambda_max=None, mode="parity", refill_threshold=0, image_width=0, device=0, out=None):
+    """`trace` with float32 [N,3] host arrays in and out (Blender's native precision): FP64 integration of the exactly
+    widened inputs, results rounded once to float32; 28 B/ray over PCIe instead of 100.  Returns
+    (exit_pos f32, exit_dir f32, status i32)."""
+    params = make_params(M, r_sphere, rtol, atol, max_step, eps_horizon, lambda_max, mode, refill_threshold,
+                         image_width)
+    pos = np.ascontiguousarray(entry_pos, dtype=np.float32)
+    dirs = np.ascontiguousarray(entry_dir, dtype=np.float32)
+    if pos.ndim != 2 or pos.shape[1] != 3 or dirs.shape != pos.shape:
+        raise ValueError(f"entry_pos and entry_dir must both be [N,3]; got {pos.shape} and {dirs.shape}")
+    n = pos.shape[0]
+    if out is not None:
+        exit_pos, exit_dir, status = out
+    else:
+        exit_pos, exit_dir = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+        status = np.empty(n, np.int32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    _lib.check(_lib.load().bhg_trace_schwarzschild_f32io_host(p(pos), p(dirs), p(exit_pos), p(exit_dir), p(status), n,
+                                                              ctypes.byref(params), int(device)))
+    return exit_pos, exit_dir, status
+
+
 def sky_uv(exit_dir, status=None):
     """Equirectangular sky-lookup coordinates of exit directions (the arithmetic of the reference's
     background_hit, RelativisticRenderEngine.py:366-378): float32 [N,2] = (-phi, 2 theta - 1); NaN where `status`

@@ -132,7 +132,7 @@ struct DeviceCtx {
     std::mutex mu;
     bool ready = false;
     int sm_count = 0;
-    int blocks_per_sm[2][2] = {{0, 0}, {0, 0}};  // [mode][layout]
+    int blocks_per_sm[2][3] = {{0, 0, 0}, {0, 0, 0}};  // [mode][layout]
     unsigned long long* queue_slots = nullptr;   // kQueueSlots work-queue heads
     std::atomic<unsigned> next_slot{0};
     // staging buffers of the host entry point (grow-only)
@@ -176,6 +176,8 @@ int ensure_device(int device, DeviceCtx** out) {
         int rc;
         if ((rc = query_occupancy<4, bhg::IN_SOA>(&c.blocks_per_sm[0][0]))) return rc;
         if ((rc = query_occupancy<4, bhg::IN_AOS>(&c.blocks_per_sm[0][1]))) return rc;
+        if ((rc = query_occupancy<4, bhg::IN_AOS_F32>(&c.blocks_per_sm[0][2]))) return rc;
+        if ((rc = query_occupancy<3, bhg::IN_AOS_F32>(&c.blocks_per_sm[1][2]))) return rc;
         if ((rc = query_occupancy<3, bhg::IN_SOA>(&c.blocks_per_sm[1][0]))) return rc;
         if ((rc = query_occupancy<3, bhg::IN_AOS>(&c.blocks_per_sm[1][1]))) return rc;
         BHG_CUDA(cudaMalloc(&c.queue_slots, kQueueSlots * sizeof(unsigned long long)));
@@ -240,7 +242,7 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
     if (disk && p->mode != BHG_MODE_PARITY)
         return fail(BHG_ERR_INVALID_ARGUMENT, "the disk-crossing event is available in parity mode only");
     if (disk && in_kind != bhg::IN_AOS)
-        return fail(BHG_ERR_INVALID_ARGUMENT, "the disk-crossing event needs the AOS layout");
+        return fail(BHG_ERR_INVALID_ARGUMENT, "the disk-crossing event needs the float64 AOS layout");
     bhg::TraceArgs a;
     memset(&a, 0, sizeof(a));
     a.in = in; a.in_dir = in_dir; a.out = out; a.out_dir = out_dir;
@@ -272,9 +274,11 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
         bhg::trace_kernel<4, bhg::IN_AOS, true><<<blocks, BHG_BLOCK, 0, stream>>>(a);
     } else if (mode == BHG_MODE_PARITY) {
         if (in_kind == bhg::IN_AOS) bhg::trace_kernel<4, bhg::IN_AOS><<<blocks, BHG_BLOCK, 0, stream>>>(a);
+        else if (in_kind == bhg::IN_AOS_F32) bhg::trace_kernel<4, bhg::IN_AOS_F32><<<blocks, BHG_BLOCK, 0, stream>>>(a);
         else bhg::trace_kernel<4, bhg::IN_SOA><<<blocks, BHG_BLOCK, 0, stream>>>(a);
     } else {
         if (in_kind == bhg::IN_AOS) bhg::trace_kernel<3, bhg::IN_AOS><<<blocks, BHG_BLOCK, 0, stream>>>(a);
+        else if (in_kind == bhg::IN_AOS_F32) bhg::trace_kernel<3, bhg::IN_AOS_F32><<<blocks, BHG_BLOCK, 0, stream>>>(a);
         else bhg::trace_kernel<3, bhg::IN_SOA><<<blocks, BHG_BLOCK, 0, stream>>>(a);
     }
     g_launches.fetch_add(1);
@@ -496,6 +500,57 @@ int bhg_trace_schwarzschild_f64_host_ex(const double* entry_pos, const double* e
         const long long nchunks = idx;
         for (long long j = (nchunks >= 2 ? nchunks - 2 : 0); j < nchunks; j++)
             if ((rc = drain(j * chunk, (int)(j % 3)))) return rc;
+    }
+    for (auto& s : c->streams) BHG_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int bhg_trace_schwarzschild_f32io(const float* entry_pos, const float* entry_dir, float* exit_pos, float* exit_dir,
+                                  int32_t* status, int32_t* counters, int64_t n, const bhg_params* params,
+                                  int32_t device, void* stream) {
+    DeviceRestore restore_device_on_exit;
+    int rc = validate(params, n);
+    if (rc) return rc;
+    if (n > 0 && (!entry_pos || !entry_dir || !exit_dir || !status)) return fail(BHG_ERR_INVALID_ARGUMENT, "NULL ray buffer");
+    DeviceCtx* c;
+    if ((rc = ensure_device(device, &c))) return rc;
+    return launch_trace(*c, (const double*)entry_pos, (const double*)entry_dir, (double*)exit_pos, (double*)exit_dir,
+                        status, counters, nullptr, n, bhg::IN_AOS_F32, params->image_width, params, (cudaStream_t)stream);
+}
+
+int bhg_trace_schwarzschild_f32io_host(const float* entry_pos, const float* entry_dir, float* exit_pos, float* exit_dir,
+                                       int32_t* status, int64_t n, const bhg_params* params, int32_t device) {
+    DeviceRestore restore_device_on_exit;
+    int rc = validate(params, n);
+    if (rc) return rc;
+    if (n > 0 && (!entry_pos || !entry_dir || !exit_pos || !exit_dir || !status))
+        return fail(BHG_ERR_INVALID_ARGUMENT, "NULL ray buffer");
+    DeviceCtx* c;
+    if ((rc = ensure_device(device, &c))) return rc;
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(c->host_mu);
+    const size_t vec = (size_t)n * 3 * sizeof(float);
+    if ((rc = ensure_stage(c, 4 * vec + (size_t)n * sizeof(int32_t) + 1024))) return rc;
+    char* base = (char*)c->stage;
+    float* d_pin = (float*)base;
+    float* d_din = (float*)(base + vec);
+    float* d_pout = (float*)(base + 2 * vec);
+    float* d_dout = (float*)(base + 3 * vec);
+    int32_t* d_status = (int32_t*)(base + 4 * vec);
+    const long long chunk = pick_chunk(n, params->image_width > 0 ? 4LL * params->image_width : 0, 1 << 19);
+    int si = 0;
+    for (long long b = 0; b < n; b += chunk, si = (si + 1) % 3) {
+        const long long m = (n - b < chunk) ? (n - b) : chunk;
+        cudaStream_t s = c->streams[si];
+        BHG_CUDA(cudaMemcpyAsync(d_pin + 3 * b, entry_pos + 3 * b, (size_t)m * 12, cudaMemcpyHostToDevice, s));
+        BHG_CUDA(cudaMemcpyAsync(d_din + 3 * b, entry_dir + 3 * b, (size_t)m * 12, cudaMemcpyHostToDevice, s));
+        rc = launch_trace(*c, (const double*)(d_pin + 3 * b), (const double*)(d_din + 3 * b), (double*)(d_pout + 3 * b),
+                          (double*)(d_dout + 3 * b), d_status + b, nullptr, nullptr, m, bhg::IN_AOS_F32,
+                          params->image_width, params, s);
+        if (rc) return rc;
+        BHG_CUDA(cudaMemcpyAsync(exit_pos + 3 * b, d_pout + 3 * b, (size_t)m * 12, cudaMemcpyDeviceToHost, s));
+        BHG_CUDA(cudaMemcpyAsync(exit_dir + 3 * b, d_dout + 3 * b, (size_t)m * 12, cudaMemcpyDeviceToHost, s));
+        BHG_CUDA(cudaMemcpyAsync(status + b, d_status + b, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
     }
     for (auto& s : c->streams) BHG_CUDA(cudaStreamSynchronize(s));
     return 0;

@@ -41,8 +41,10 @@ struct TraceArgs {
     double* disk_xy;  // [n][2], NaN = no hit
 };
 
-// memory layout of the ray buffers
-constexpr int IN_SOA = 0, IN_AOS = 1;
+// memory layout of the ray buffers.  IN_AOS_F32: the same [n][3] arrays stored as float32 (Blender's mathutils
+// vectors are float32, RelativisticRenderEngine.py:181-182,223): converted to FP64 on load, integrated in FP64,
+// rounded to float32 on store - half the PCIe / HBM bytes.
+constexpr int IN_SOA = 0, IN_AOS = 1, IN_AOS_F32 = 2;
 // A NaN entry position marks a primary ray that never meets the sphere of influence (written by
 // generate_rays_kernel): it is not integrated, keeps its flat direction and gets this status.
 constexpr int MISSED_SPHERE = 5;
@@ -69,7 +71,15 @@ constexpr int PEND_HE = -5;  // both
 // returns false for a ray flagged as missing the sphere (NaN entry position; k holds its flat direction)
 template <int IN>
 __device__ __forceinline__ bool load_ray(const TraceArgs& a, long long idx, double (&x)[3], double (&k)[3]) {
-    if (IN == IN_AOS) {
+    if (IN == IN_AOS_F32) {
+        const float* pf = reinterpret_cast<const float*>(a.in);
+        const float* df = reinterpret_cast<const float*>(a.in_dir);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            x[c] = (double)__ldg(pf + 3 * idx + c);
+            k[c] = (double)__ldg(df + 3 * idx + c);
+        }
+    } else if (IN == IN_AOS) {
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             x[c] = __ldg(a.in + 3 * idx + c);
@@ -89,7 +99,15 @@ __device__ __forceinline__ bool load_ray(const TraceArgs& a, long long idx, doub
 template <int IN>
 __device__ __forceinline__ void store_ray(const TraceArgs& a, long long idx, const double (&x)[3],
                                           const double (&k)[3], int status, int n_attempt, int n_accept) {
-    if (IN != IN_SOA) {
+    if (IN == IN_AOS_F32) {
+        float* pf = reinterpret_cast<float*>(a.out);
+        float* df = reinterpret_cast<float*>(a.out_dir);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            if (pf) pf[3 * idx + c] = (float)x[c];
+            df[3 * idx + c] = (float)k[c];
+        }
+    } else if (IN == IN_AOS) {
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             if (a.out) a.out[3 * idx + c] = x[c];

@@ -125,6 +125,17 @@ int bhg_trace_schwarzschild_f64_host(const double* entry_pos, const double* entr
                                      double* exit_dir, int32_t* status, int32_t* counters, int64_t n,
                                      const bhg_params* params, int32_t device);
 
+/* float32 I/O variants: entry_pos / entry_dir / exit_pos / exit_dir are [n][3] float32 (Blender's mathutils vectors
+ * and image buffers are float32: RelativisticRenderEngine.py:181-182,223).  Inputs are widened exactly to FP64, the
+ * integration is the same FP64 algorithm, results are rounded once to float32.  28 B/ray cross PCIe instead of 100.
+ * _f32io: device buffers, asynchronous on `stream` (exit_pos may be NULL); _f32io_host: host buffers (pinned for full
+ * speed), returns when the results are in place. */
+int bhg_trace_schwarzschild_f32io(const float* entry_pos, const float* entry_dir, float* exit_pos, float* exit_dir,
+                                  int32_t* status, int32_t* counters, int64_t n, const bhg_params* params,
+                                  int32_t device, void* stream);
+int bhg_trace_schwarzschild_f32io_host(const float* entry_pos, const float* entry_dir, float* exit_pos, float* exit_dir,
+                                       int32_t* status, int64_t n, const bhg_params* params, int32_t device);
+
 /* Pinhole camera of the reference's render loop: replaces the per-pixel direction construction of
  * RelativisticRenderEngine.ray_trace (RRE.py:185-189,195-230: loop order s -> y -> x, pixel offsets, jitter,
  * rotation by the camera matrix, normalisation) and the flat-space hit on the "isBH" sphere
