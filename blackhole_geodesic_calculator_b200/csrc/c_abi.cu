@@ -269,6 +269,10 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
     const int mode = p->mode;
     long long want_blocks = (n + BHG_BLOCK - 1) / BHG_BLOCK;
     long long max_blocks = (long long)c.sm_count * c.blocks_per_sm[mode][in_kind];
+    if (const char* e = getenv("BHG_BLOCKS_PER_SM")) {  // tuning experiments: fewer resident warps
+        int v = atoi(e);
+        if (v > 0 && v < c.blocks_per_sm[mode][in_kind]) max_blocks = (long long)c.sm_count * v;
+    }
     int blocks = (int)(want_blocks < max_blocks ? want_blocks : max_blocks);
     if (disk) {
         bhg::trace_kernel<4, bhg::IN_AOS, true><<<blocks, BHG_BLOCK, 0, stream>>>(a);
