@@ -120,15 +120,9 @@ __device__ __forceinline__ double inv_tenth_root(double a) {
     return res;
 }
 
-// max(|a|, |b|) on the integer pipe: for finite doubles the order of |x| is the order of its bit pattern.
-// (A NaN compares largest and propagates, which only ever turns an already-NaN error norm NaN.)
-__device__ __forceinline__ double abs_max(double a, double b) {
-    // written on the 32-bit halves so that the compiler cannot turn it back into FP64-pipe |x| operations
-    const int ha = __double2hiint(a) & 0x7fffffff, hb = __double2hiint(b) & 0x7fffffff;
-    const unsigned la = (unsigned)__double2loint(a), lb = (unsigned)__double2loint(b);
-    const bool a_ge = (ha > hb) || (ha == hb && la >= lb);
-    return __hiloint2double(a_ge ? ha : hb, (int)(a_ge ? la : lb));
-}
+// max(|a|, |b|): one FP64 compare with |.| modifiers plus two selects (a 7-instruction integer-pipe version
+// measured the same, profiles/r1m_experiments.txt).
+__device__ __forceinline__ double abs_max(double a, double b) { return fmax(fabs(a), fabs(b)); }
 
 // a^(1/5) for a in [1e-30, 1e30] (initial-step heuristic): Newton on x^-5 = a for the inverse root, then
 // a * x^4.  Float seed 1e-5 -> two steps -> 1e-18.
