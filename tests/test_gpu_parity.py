@@ -398,3 +398,29 @@ def test_float32_io_variant(api):
     assert ok.mean() > 0.98
     dev = np.abs(ep[ok] - g["exit_pos"][ok]).max(axis=1) / 60.0
     assert np.median(dev) < 1e-6 and np.percentile(dev, 90) < 1e-4
+
+
+def test_flat_limit_and_concurrent_callers(api):
+    """M -> 0 gives straight chords; two host threads may call the library at the same time (ctypes drops the GIL)."""
+    import threading
+    from blackhole_geodesic_calculator_b200 import raygen
+    pos, d = raygen.config_bundle(64, 64, 1)
+    ep, ed, st = api.trace(pos, d, M=1e-9, rtol=1e-10, atol=1e-12)
+    chord = -2 * np.sum(pos * d, axis=1)
+    assert (st == 0).all()
+    assert np.abs(ep - (pos + chord[:, None] * d)).max() < 1e-5 and np.abs(ed - d).max() < 1e-7
+    g = load_golden("cfg1_64x64.npz")
+    results = [None, None]
+
+    def work(i):
+        for _ in range(5):
+            results[i] = api.trace(g["entry_pos"], g["entry_dir"])
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for r in results:
+        assert np.array_equal(r[2], g["status"])
+        assert np.array_equal(r[0], results[0][0], equal_nan=True)
