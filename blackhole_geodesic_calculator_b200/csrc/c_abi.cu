@@ -261,7 +261,7 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
         int v = atoi(e);
         if (v > 0) a.idle_budget = v;
     }
-    a.tile_width = (image_width > 0 && image_width % 8 == 0 && n % (4LL * image_width) == 0 && !order) ? image_width : 0;
+    a.tile_width = (image_width > 0 && image_width % 4 == 0 && n % (8LL * image_width) == 0 && !order) ? image_width : 0;
     if (disk) { a.disk_r_in = ex->disk_r_in; a.disk_r_out = ex->disk_r_out; a.disk_xy = ex->disk_xy; }
     unsigned slot = c.next_slot.fetch_add(1) % kQueueSlots;
     a.queue_head = c.queue_slots + slot;
@@ -302,8 +302,8 @@ int launch_generate(DeviceCtx& c, const bhg::Camera& cam, long long n, double* p
     return 0;
 }
 
-// the tile hint of a camera call: valid only when the call starts on a 4-row band boundary
-int camera_image_width(const bhg::Camera& cam) { return (cam.first_ray % (4LL * cam.width) == 0) ? cam.width : 0; }
+// the tile hint of a camera call: valid only when the call starts on an 8-row band boundary
+int camera_image_width(const bhg::Camera& cam) { return (cam.first_ray % (8LL * cam.width) == 0) ? cam.width : 0; }
 
 // rays per pipeline chunk of the host entry points; BHG_CHUNK_RAYS overrides (tuning)
 // (measured on B200, profiles/r1g_chunks.txt: 512 Ki rays is best when rays also travel H2D, 256 Ki when only
@@ -315,7 +315,7 @@ long long pick_chunk(long long n, long long band, long long big = 1 << 18) {
         if (v > 0) chunk = v;
     }
     if (chunk > n) chunk = n;
-    if (band > 0 && n > chunk) chunk = ((chunk + band - 1) / band) * band;  // whole 4-row bands keep the tile hint
+    if (band > 0 && n > chunk) chunk = ((chunk + band - 1) / band) * band;  // whole 8-row bands keep the tile hint
     return chunk;
 }
 
@@ -414,7 +414,7 @@ int bhg_trace_schwarzschild_f64_host_ex(const double* entry_pos, const double* e
     const bool bounce = is_pageable(entry_pos) || is_pageable(entry_dir) || is_pageable(exit_pos) ||
                         is_pageable(exit_dir) || is_pageable(status) || is_pageable(counters) ||
                         (disk && is_pageable(extras->disk_xy));
-    const long long chunk = pick_chunk(n, params->image_width > 0 ? 4LL * params->image_width : 0, bounce ? 1 << 18 : 1 << 19);
+    const long long chunk = pick_chunk(n, params->image_width > 0 ? 8LL * params->image_width : 0, bounce ? 1 << 18 : 1 << 19);
     // per-slot bounce layout: pos_in | dir_in | pos_out | dir_out | disk | status | counters(2)
     const size_t slot_bytes = (size_t)chunk * (24 * 4 + 16 + 4 * 3) + 256;
     char* bb = nullptr;
@@ -541,7 +541,7 @@ int bhg_trace_schwarzschild_f32io_host(const float* entry_pos, const float* entr
     float* d_pout = (float*)(base + 2 * vec);
     float* d_dout = (float*)(base + 3 * vec);
     int32_t* d_status = (int32_t*)(base + 4 * vec);
-    const long long chunk = pick_chunk(n, params->image_width > 0 ? 4LL * params->image_width : 0, 1 << 19);
+    const long long chunk = pick_chunk(n, params->image_width > 0 ? 8LL * params->image_width : 0, 1 << 19);
     int si = 0;
     for (long long b = 0; b < n; b += chunk, si = (si + 1) % 3) {
         const long long m = (n - b < chunk) ? (n - b) : chunk;
@@ -616,8 +616,8 @@ int bhg_trace_camera_f64_host(const bhg_camera* cam, double* exit_pos, double* e
     double* d_dout = (double*)(base + 3 * vec);
     int32_t* d_status = (int32_t*)(base + 4 * vec);
     int32_t* d_cnt = d_status + n;
-    // chunks are whole 4-row bands so that every chunk keeps the 8 x 4 tile scheduling
-    const long long chunk = pick_chunk(n, 4LL * cam->width);
+    // chunks are whole 8-row bands so that every chunk keeps the tile scheduling
+    const long long chunk = pick_chunk(n, 8LL * cam->width);
     int si = 0;
     for (long long b = 0; b < n; b += chunk, si = (si + 1) % 3) {
         const long long m = (n - b < chunk) ? (n - b) : chunk;
@@ -676,7 +676,7 @@ int bhg_trace_camera_sky_host(const bhg_camera* cam, float* uv, int32_t* status,
     double* d_dout = (double*)(base + 2 * vec);
     float* d_uv = (float*)(base + 3 * vec);
     int32_t* d_status = (int32_t*)(base + 3 * vec + (size_t)n * 8);
-    const long long chunk = pick_chunk(n, 4LL * cam->width);
+    const long long chunk = pick_chunk(n, 8LL * cam->width);
     int si = 0;
     for (long long b = 0; b < n; b += chunk, si = (si + 1) % 3) {
         const long long m = (n - b < chunk) ? (n - b) : chunk;

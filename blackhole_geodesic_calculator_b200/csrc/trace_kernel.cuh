@@ -35,7 +35,7 @@ struct TraceArgs {
     int idle_budget;       // used when refill_threshold == 0: service when the idle lane-iterations accumulated
                            // since the last service reach this budget ("ski rental": idle until the waste equals
                            // the price of one service), which adapts to coherent and incoherent batches alike
-    int tile_width;  // > 0: queue slots enumerate 8 x 4 pixel tiles of a row-major image of this width
+    int tile_width;  // > 0: queue slots enumerate 4 x 8 pixel tiles of a row-major image of this width
     // DISK variant only: first crossing of the equatorial plane with disk_r_in <= r <= disk_r_out
     double disk_r_in, disk_r_out;
     double* disk_xy;  // [n][2], NaN = no hit
@@ -50,15 +50,17 @@ constexpr int IN_SOA = 0, IN_AOS = 1, IN_AOS_F32 = 2;
 constexpr int MISSED_SPHERE = 5;
 
 // queue slot -> ray index.  With the image hint, 32 consecutive slots (one warp's fetch when it starts empty)
-// cover an 8 x 4 pixel tile, whose rays have far more similar step counts than 32 pixels of one row.
+// cover a 4 x 8 pixel tile, whose rays have far more similar step counts than 32 pixels of one row.
 __device__ __forceinline__ long long slot_to_ray(const TraceArgs& a, long long slot) {
     if (a.order) return (long long)__ldg(a.order + slot);
     if (a.tile_width > 0) {
-        const long long band_sz = 4LL * a.tile_width;           // 4 image rows
+        // tiles 4 pixels wide x 8 tall (bands of 8 image rows); measured against 8 wide x 4 tall: config 2
+        // 3.463 vs 3.504 ms, config 3 equal (profiles/r1m_experiments.txt)
+        const long long band_sz = 8LL * a.tile_width;
         const long long band = slot / band_sz;
         const int t = (int)(slot - band * band_sz);
         const int tile = t >> 5, l = t & 31;
-        return band * band_sz + (long long)(l >> 3) * a.tile_width + (tile << 3) + (l & 7);
+        return band * band_sz + (long long)(l >> 2) * a.tile_width + (tile << 2) + (l & 3);
     }
     return slot;
 }

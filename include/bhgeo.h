@@ -74,8 +74,8 @@ typedef struct bhg_params {
                                  refill once the idle lane-iterations since the last refill reach a fixed budget */
     int32_t image_width;      /* coherence hint: the rays are a row-major image (or stack of images) of this
                                  width, as the reference's s -> y -> x loop produces them (RRE.py:195-218); the
-                                 queue then hands every warp an 8 x 4 pixel tile instead of 32 pixels of one row.
-                                 0 = no hint.  Ignored unless image_width % 8 == 0 and n % (4 image_width) == 0.
+                                 queue then hands every warp a 4 x 8 pixel tile instead of 32 pixels of one row.
+                                 0 = no hint.  Ignored unless image_width % 4 == 0 and n % (8 image_width) == 0.
                                  Scheduling only: results are bit-identical with and without the hint.       */
     int32_t reserved;         /* must be 0 */
 } bhg_params;
