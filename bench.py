@@ -217,12 +217,19 @@ def run_b200(args):
     att, acc, integ = api.sum_counters(counters.data_ptr(), status.data_ptr(), n, local, stream.cuda_stream)
     flop_per_launch = FLOP_FIXED * integ + FLOP_PER_ATTEMPT * att
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
+    # clocks are sampled from before the warm-up to the end of the timed region (same load throughout); the warm-up
+    # runs at least W steps and at least 0.4 s so that nvidia-smi is up and several samples fall under load
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    t_w = time.perf_counter()
+    n_w = 0
+    while n_w < max(args.warmup, 3) or time.perf_counter() - t_w < 0.4:
+        step()
+        n_w += 1
+        if n_w % 8 == 0:
+            torch.cuda.synchronize(dev)
+    barrier()
     launches0 = api.launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
@@ -336,7 +343,8 @@ def run_b200(args):
         peak = peak_tf or NOMINAL_FP64_TFLOPS
         line = {
             "metric": "geodesic rays/s (1024^2 x 5 spp Schwarzschild frame)", "value": value, "unit": "rays/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "warmup_steps_run": n_w,
+            "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "config 2: 1024x1024x5spp Schwarzschild frame (5242880 rays/GPU/step), M=1, "
                                    "r_sphere=60M, rtol=1e-3, atol=1e-6, camera (120,-80,40)M fov 0.6, Philox jitter "
