@@ -48,7 +48,9 @@ class BhgCamera(ctypes.Structure):
 
 class BhgExtras(ctypes.Structure):
     """Mirror of `struct bhg_extras` (include/bhgeo.h)."""
-    _fields_ = [("disk_r_in", ctypes.c_double), ("disk_r_out", ctypes.c_double), ("disk_xy", ctypes.c_void_p)]
+    _fields_ = [("disk_r_in", ctypes.c_double), ("disk_r_out", ctypes.c_double), ("disk_xy", ctypes.c_void_p),
+                ("poly_n", ctypes.c_int32), ("reserved", ctypes.c_int32), ("poly_xyz", ctypes.c_void_p),
+                ("poly_count", ctypes.c_void_p)]
 
 
 class BhgError(RuntimeError):

@@ -10,9 +10,9 @@ reference's call sites, and adds a `*_batch` method that does a whole frame or t
   * `RelativisticCamera.run` / `.ray_blackhole_hit` / `.ray_end`
                                                        <- raytracer/RelativisticRenderEngineCamEdition.py:206-215,225-228
 
-Out of scope here (SURVEY.md section 8f "next" row 2): the dense trajectory polylines that `checkHitDisk`
-(LimitedRelativisticRenderEngine.py:413-438) scans; the polyline outputs below hold the entry and end states
-only.
+Trajectory polylines (what `checkHitDisk`, LimitedRelativisticRenderEngine.py:413-438, scans and what
+`calc_trajectory(nr_points_curve=...)` returns) are sampled in flight on linspace(0, curve_end, N) up to the
+termination time, like solve_ivp's t_eval does for the reference.
 """
 from __future__ import annotations
 
@@ -47,14 +47,26 @@ class GeodesicIntegratorSchwarzschild:
         return exit_dir, exit_pos, status == api.CAPTURED, status == api.START_INSIDE_HOLE, status
 
     def calc_trajectory(self, k0_xyz, x0_xyz, max_step=math.inf, curve_end=50.0, nr_points_curve=50, verbose=False):
-        """Per-ray drop-in: returns (k_xyz[3,2], x_xyz[3,2], result) — columns are the start and the end state
-        (the reference engine reads column -1 only, RelativisticRenderEngine.py:307-308)."""
+        """Per-ray drop-in: returns (k_xyz[3,N'], x_xyz[3,N'], result).  x_xyz holds the trajectory sampled on
+        linspace(0, curve_end, nr_points_curve) up to the termination time (N' <= nr_points_curve), as curvedpy
+        returns it (RelativisticRenderEngine.py:293-294,299-300); k_xyz holds the start direction in column 0 and
+        the unit end direction in column -1 (the only column the engine reads, RRE.py:307-308), NaN in between."""
         k0 = np.asarray(k0_xyz, dtype=np.float64).reshape(1, 3)
         x0 = np.asarray(x0_xyz, dtype=np.float64).reshape(1, 3)
-        end_dir, end_loc, hit, inside, status = self.calc_trajectories_batch(k0, x0, max_step, curve_end)
-        result = {"start_inside_hole": bool(inside[0]), "hit_blackhole": bool(hit[0]), "status": int(status[0])}
-        k_xyz = np.stack([k0[0], end_dir[0]], axis=1)
-        x_xyz = np.stack([x0[0], end_loc[0]], axis=1)
+        ms = math.inf if (max_step is None or max_step == -1) else float(max_step)
+        ep, ed, st, poly, cnt = api.trace(x0, k0, self.mass, math.inf, self.rtol, self.atol, max_step=ms,
+                                          eps_horizon=self.eps_horizon, lambda_max=float(curve_end),
+                                          device=self.device, polyline=max(2, int(nr_points_curve)))
+        status = int(st[0])
+        result = {"start_inside_hole": status == api.START_INSIDE_HOLE, "hit_blackhole": status == api.CAPTURED,
+                  "status": status}
+        c = max(int(cnt[0]), 1)
+        x_xyz = poly[0, :c].T.copy()
+        if status == api.START_INSIDE_HOLE:
+            x_xyz = x0.T.copy()
+        k_xyz = np.full_like(x_xyz, np.nan)
+        k_xyz[:, 0] = k0[0]
+        k_xyz[:, -1] = ed[0]
         return k_xyz, x_xyz, result
 
 
@@ -130,17 +142,28 @@ class SchwarzschildGeodesic:
         return hit, texture_x, scale, intensity
 
     def ray_trace(self, direction, loc_hit, exit_tolerance=0.2, ratio_obj_to_blackhole=30.0, curve_end=None,
-                  max_step=math.inf, warnings=False):
-        """Per-ray drop-in: (x, y, z, end_loc, end_dir, mes); x, y, z hold the entry and end points."""
-        end_loc, end_dir, hit_bh, outside, status = self.ray_trace_batch(
-            np.asarray(direction, float).reshape(1, 3), np.asarray(loc_hit, float).reshape(1, 3), exit_tolerance,
-            ratio_obj_to_blackhole, curve_end, max_step)
-        mes = {"hit_blackhole": bool(hit_bh[0]), "status": int(status[0])}
-        if outside[0]:
+                  max_step=math.inf, warnings=False, nr_points_curve=256):
+        """Per-ray drop-in: (x, y, z, end_loc, end_dir, mes).  x, y, z are the trajectory polyline in r_s units
+        (the unit in which the engine's checkHitDisk compares radii with disk_R_in * ratio,
+        LimitedRelativisticRenderEngine.py:283-285), sampled on linspace(0, curve_end, nr_points_curve) up to the
+        exit / capture, with the exact end point appended."""
+        d = np.asarray(direction, float).reshape(1, 3)
+        p = np.asarray(loc_hit, float).reshape(1, 3)
+        ratio = float(ratio_obj_to_blackhole)
+        scale = ratio / np.linalg.norm(p[0])
+        lam = self.approximateCurveEnd(ratio) if curve_end is None else float(curve_end)
+        ms = math.inf if (max_step is None or max_step == -1) else float(max_step)
+        ep, ed, st, poly, cnt = api.trace(p * scale, d, 0.5, ratio, self.rtol, self.atol, max_step=ms,
+                                          eps_horizon=self.eps_horizon, lambda_max=lam, device=self.device,
+                                          polyline=max(2, int(nr_points_curve)))
+        status = int(st[0])
+        hit_bh = status == api.CAPTURED
+        off = abs(np.linalg.norm(ep[0]) - ratio) > exit_tolerance
+        mes = {"hit_blackhole": hit_bh, "status": status}
+        if not hit_bh and (off or status != api.ESCAPED):
             mes["error"] = "Outside"
-        loc = np.asarray(loc_hit, float).reshape(3)
-        xyz = np.stack([loc, end_loc[0]], axis=1)
-        return xyz[0], xyz[1], xyz[2], end_loc[0], end_dir[0], mes
+        pts = np.vstack([poly[0, :int(cnt[0])], ep[0][None, :]])
+        return pts[:, 0], pts[:, 1], pts[:, 2], ep[0] / scale, ed[0], mes
 
 
 class RelativisticCamera:

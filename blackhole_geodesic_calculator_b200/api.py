@@ -45,7 +45,7 @@ def _is_torch(x):
 
 def trace(entry_pos, entry_dir, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, *, max_step=math.inf,
           eps_horizon=0.01, lambda_max=None, mode="parity", refill_threshold=0, image_width=0, device=0,
-          return_counters=False, disk=None, out=None):
+          return_counters=False, disk=None, out=None, polyline=None):
     """Integrate N Schwarzschild null geodesics from sphere entry to exit or capture.
 
     entry_pos, entry_dir : [N,3] float64, BH-centred position and coordinate direction (numpy arrays on the
@@ -57,12 +57,17 @@ def trace(entry_pos, entry_dir, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, *, m
     disk : optional (r_in, r_out): also return disk_xy[N,2], the first crossing of the equatorial plane z = 0
         with r_in <= r <= r_out (NaN = none) — the in-flight form of the reference's checkHitDisk
         (LimitedRelativisticRenderEngine.py:413-438).  Parity mode only.
+    polyline : optional K >= 2 (needs an explicit lambda_max): also return (poly_xyz[N,K,3], poly_count[N]), the
+        positions at lambda = linspace(0, lambda_max, K) up to each ray's termination (NaN beyond) - what curvedpy
+        returns for nr_points_curve (RelativisticRenderEngine.py:293-294).  Parity mode, numpy inputs.
     Returns (exit_pos[N,3], exit_dir[N,3] unit-norm, status[N] int32) and, with return_counters, an
-    int32 [2,N] array of (RK45 attempts, accepted steps), then disk_xy if requested.
+    int32 [2,N] array of (RK45 attempts, accepted steps), then disk_xy, then (poly_xyz, poly_count) if requested.
     """
     params = make_params(M, r_sphere, rtol, atol, max_step, eps_horizon, lambda_max, mode, refill_threshold,
                          image_width)
     if _is_torch(entry_pos):
+        if polyline is not None:
+            raise ValueError("polyline output is available for numpy inputs")
         return _trace_torch(entry_pos, entry_dir, params, return_counters, disk)
     lib = _lib.load()
     pos = np.ascontiguousarray(entry_pos, dtype=np.float64)
@@ -82,7 +87,17 @@ def trace(entry_pos, entry_dir, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, *, m
     counters = np.empty((2, n), dtype=np.int32) if return_counters else None
     p = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
     disk_xy = np.empty((n, 2), dtype=np.float64) if disk is not None else None
-    extras = BhgExtras(float(disk[0]), float(disk[1]), disk_xy.ctypes.data) if disk is not None else None
+    extras = None
+    if disk is not None or polyline is not None:
+        extras = BhgExtras()
+        if disk is not None:
+            extras.disk_r_in, extras.disk_r_out, extras.disk_xy = float(disk[0]), float(disk[1]), disk_xy.ctypes.data
+        if polyline is not None:
+            if int(polyline) < 2 or lambda_max is None:
+                raise ValueError("polyline needs K >= 2 samples and an explicit lambda_max")
+            poly_xyz = np.full((n, int(polyline), 3), np.nan, dtype=np.float64)
+            poly_count = np.zeros(n, dtype=np.int32)
+            extras.poly_n, extras.poly_xyz, extras.poly_count = int(polyline), poly_xyz.ctypes.data, poly_count.ctypes.data
     _lib.check(lib.bhg_trace_schwarzschild_f64_host_ex(p(pos), p(dirs), p(exit_pos), p(exit_dir), p(status),
                                                        p(counters), n, ctypes.byref(params),
                                                        ctypes.byref(extras) if extras is not None else None,
@@ -92,6 +107,8 @@ def trace(entry_pos, entry_dir, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, *, m
         res += (counters,)
     if disk is not None:
         res += (disk_xy,)
+    if polyline is not None:
+        res += (poly_xyz, poly_count)
     return res
 
 

@@ -239,6 +239,9 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
                  const bhg_params* p, cudaStream_t stream, const bhg_extras* ex = nullptr) {
     if (n == 0) return 0;
     const bool disk = ex && ex->disk_xy && ex->disk_r_out > 0.0;
+    const bool poly = ex && ex->poly_n >= 2 && ex->poly_xyz && ex->poly_count;
+    if (poly && (p->mode != BHG_MODE_PARITY || in_kind != bhg::IN_AOS || !(p->lambda_max > 0.0)))
+        return fail(BHG_ERR_INVALID_ARGUMENT, "the polyline output needs parity mode, the float64 AOS layout and an explicit lambda_max");
     if (disk && p->mode != BHG_MODE_PARITY)
         return fail(BHG_ERR_INVALID_ARGUMENT, "the disk-crossing event is available in parity mode only");
     if (disk && in_kind != bhg::IN_AOS)
@@ -263,6 +266,12 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
     }
     a.tile_width = (image_width > 0 && image_width % 4 == 0 && n % (8LL * image_width) == 0 && !order) ? image_width : 0;
     if (disk) { a.disk_r_in = ex->disk_r_in; a.disk_r_out = ex->disk_r_out; a.disk_xy = ex->disk_xy; }
+    if (poly) {
+        a.poly_n = ex->poly_n;
+        a.poly_dt = a.lambda_max / (ex->poly_n - 1);
+        a.poly_xyz = ex->poly_xyz;
+        a.poly_count = ex->poly_count;
+    }
     unsigned slot = c.next_slot.fetch_add(1) % kQueueSlots;
     a.queue_head = c.queue_slots + slot;
     BHG_CUDA(cudaMemsetAsync(a.queue_head, 0, sizeof(unsigned long long), stream));
@@ -274,7 +283,10 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
         if (v > 0 && v < c.blocks_per_sm[mode][in_kind]) max_blocks = (long long)c.sm_count * v;
     }
     int blocks = (int)(want_blocks < max_blocks ? want_blocks : max_blocks);
-    if (disk) {
+    if (poly) {
+        if (disk) bhg::trace_kernel<4, bhg::IN_AOS, true, true><<<blocks, BHG_BLOCK, 0, stream>>>(a);
+        else bhg::trace_kernel<4, bhg::IN_AOS, false, true><<<blocks, BHG_BLOCK, 0, stream>>>(a);
+    } else if (disk) {
         bhg::trace_kernel<4, bhg::IN_AOS, true><<<blocks, BHG_BLOCK, 0, stream>>>(a);
     } else if (mode == BHG_MODE_PARITY) {
         if (in_kind == bhg::IN_AOS) bhg::trace_kernel<4, bhg::IN_AOS><<<blocks, BHG_BLOCK, 0, stream>>>(a);
@@ -398,6 +410,50 @@ int bhg_trace_schwarzschild_f64_host_ex(const double* entry_pos, const double* e
     // device staging: pos_in | dir_in | pos_out | dir_out | status | counters
     const size_t vec = (size_t)n * 3 * sizeof(double);
     const bool disk = extras && extras->disk_xy && extras->disk_r_out > 0.0;
+    if (extras && extras->poly_n >= 2 && extras->poly_xyz && extras->poly_count) {
+        // polyline requests (small batches by nature: n x poly_n x 24 bytes come back) take a simple unpipelined path
+        cudaStream_t s0 = nullptr;
+        for (auto& st : c->streams)
+            if (!st) BHG_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        s0 = c->streams[0];
+        const size_t pbytes = (size_t)n * extras->poly_n * 24;
+        char* dbuf = nullptr;
+        const size_t tot = 4 * vec + (size_t)n * 16 + (size_t)n * 4 * 4 + pbytes + 256;
+        BHG_CUDA(cudaMallocAsync((void**)&dbuf, tot, s0));
+        double* q_pin = (double*)dbuf;
+        double* q_din = q_pin + 3 * n;
+        double* q_pout = q_din + 3 * n;
+        double* q_dout = q_pout + 3 * n;
+        double* q_disk = q_dout + 3 * n;
+        double* q_poly = q_disk + 2 * n;
+        int32_t* q_status = (int32_t*)(q_poly + (size_t)n * extras->poly_n * 3);
+        int32_t* q_cnt = q_status + n;      // 2 n
+        int32_t* q_pcount = q_cnt + 2 * n;  // n
+        bhg_extras ex = *extras;
+        ex.disk_xy = disk ? q_disk : nullptr;
+        ex.poly_xyz = q_poly;
+        ex.poly_count = q_pcount;
+        rc = 0;
+        auto cp = [&](void* d, const void* sp, size_t b, cudaMemcpyKind kd) {
+            if (!rc && cudaMemcpyAsync(d, sp, b, kd, s0) != cudaSuccess) rc = fail(BHG_ERR_CUDA, "polyline staging copy failed");
+        };
+        cp(q_pin, entry_pos, vec, cudaMemcpyHostToDevice);
+        cp(q_din, entry_dir, vec, cudaMemcpyHostToDevice);
+        // samples beyond a ray's count are not written by the kernel: all-ones bytes = NaN
+        if (!rc && cudaMemsetAsync(q_poly, 0xFF, pbytes, s0) != cudaSuccess) rc = fail(BHG_ERR_CUDA, "polyline memset failed");
+        if (!rc) rc = launch_trace(*c, q_pin, q_din, q_pout, q_dout, q_status, counters ? q_cnt : nullptr, nullptr, n,
+                                   bhg::IN_AOS, params->image_width, params, s0, &ex);
+        cp(exit_pos, q_pout, vec, cudaMemcpyDeviceToHost);
+        cp(exit_dir, q_dout, vec, cudaMemcpyDeviceToHost);
+        cp(status, q_status, (size_t)n * 4, cudaMemcpyDeviceToHost);
+        if (counters) cp(counters, q_cnt, (size_t)n * 8, cudaMemcpyDeviceToHost);
+        if (disk) cp(extras->disk_xy, q_disk, (size_t)n * 16, cudaMemcpyDeviceToHost);
+        cp(extras->poly_xyz, q_poly, pbytes, cudaMemcpyDeviceToHost);
+        cp(extras->poly_count, q_pcount, (size_t)n * 4, cudaMemcpyDeviceToHost);
+        cudaFreeAsync(dbuf, s0);
+        if (cudaStreamSynchronize(s0) != cudaSuccess && !rc) rc = fail(BHG_ERR_CUDA, "polyline trace failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return rc;
+    }
     const size_t need = 4 * vec + (size_t)n * 3 * sizeof(int32_t) + (disk ? (size_t)n * 16 : 0) + 1024;
     if ((rc = ensure_stage(c, need))) return rc;
     char* base = (char*)c->stage;

@@ -39,6 +39,11 @@ struct TraceArgs {
     // DISK variant only: first crossing of the equatorial plane with disk_r_in <= r <= disk_r_out
     double disk_r_in, disk_r_out;
     double* disk_xy;  // [n][2], NaN = no hit
+    // POLY variant only: positions sampled on linspace(0, lambda_max, poly_n) up to the termination time
+    int poly_n;
+    double poly_dt;       // lambda_max / (poly_n - 1)
+    double* poly_xyz;     // [n][poly_n][3]; samples beyond poly_count are left untouched
+    int32_t* poly_count;  // [n]
 };
 
 // memory layout of the ray buffers.  IN_AOS_F32: the same [n][3] arrays stored as float32 (Blender's mathutils
@@ -275,6 +280,37 @@ __device__ __forceinline__ bool disk_crossing(const TraceArgs& a, long long idx,
 
 // One 512-thread block per SM (16 warps, 128 registers/thread).  Measured on B200 with the same 16 warps/SM:
 // 32x16: 3.514, 64x8: 3.517, 128x4: 3.517, 256x2: 3.493, 512x1: 3.458 ms/frame (profiles/r1m_experiments.txt).
+// Polyline samples (second half): the reference asks curvedpy for nr_points_curve samples on
+// linspace(0, curve_end, N) and receives those up to the termination time (RelativisticRenderEngine.py:293-294;
+// solve_ivp t_eval semantics, scipy/_ivp/ivp.py:711-728).  Emits every pending sample time t_j <= t_end inside the
+// step that started at t_old with state (k, x): dense output of r, theta, phi -> Cartesian position.
+__device__ __forceinline__ int emit_polyline(const TraceArgs& a, long long idx, int pj, const double (&k)[4],
+                                             const double (&x)[4], const double (&K)[7][4], double t_old, double h,
+                                             double t_end) {
+    while (pj < a.poly_n) {
+        const double tj = (pj == a.poly_n - 1) ? a.lambda_max : pj * a.poly_dt;  // numpy.linspace end point is exact
+        if (!(tj <= t_end)) break;
+        double r = x[1], th = x[2], ph = x[3];
+        if (tj > t_old) {
+            const double s = (tj - t_old) / h;
+            DenseWeights w;
+            dense_weights(s, w);
+            r = dense_x(w, x[1], k[1], K[0][1], K[1][1], K[2][1], K[3][1], K[4][1], K[5][1], h);
+            th = dense_x(w, x[2], k[2], K[0][2], K[1][2], K[2][2], K[3][2], K[4][2], K[5][2], h);
+            ph = dense_x(w, x[3], k[3], K[0][3], K[1][3], K[2][3], K[3][3], K[4][3], K[5][3], h);
+        }
+        double st, ct, sp, cp;
+        sincos_tab(th, &st, &ct);
+        sincos_tab(ph, &sp, &cp);
+        double* o = a.poly_xyz + ((long long)idx * a.poly_n + pj) * 3;
+        o[0] = r * st * cp;
+        o[1] = r * st * sp;
+        o[2] = r * ct;
+        pj++;
+    }
+    return pj;
+}
+
 #ifndef BHG_MIN_BLOCKS
 #define BHG_MIN_BLOCKS 1
 #endif
@@ -282,9 +318,9 @@ __device__ __forceinline__ bool disk_crossing(const TraceArgs& a, long long idx,
 #define BHG_BLOCK 512
 #endif
 
-template <int NK, int IN, bool DISK = false>
+template <int NK, int IN, bool DISK = false, bool POLY = false>
 __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const TraceArgs a) {
-    static_assert(!DISK || NK == 4, "the disk event is defined for the spherical (parity) state");
+    static_assert(!(DISK || POLY) || NK == 4, "disk event and polyline are defined for the spherical (parity) state");
     constexpr int IR = 1;  // index of r in x
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -297,6 +333,7 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
     int n_attempt = 0, n_accept = 0;
     bool rejected = false;
     bool disk_hit = false;
+    int pj = 0;  // POLY: next polyline sample index
     bool exhausted = false;  // warp-uniform: queue has no more rays
     const int T = a.refill_threshold;
     const int B = a.idle_budget;
@@ -342,6 +379,7 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
                     if constexpr (DISK) {  // crossings before the terminal root still count
                         if (!disk_hit) disk_hit = disk_crossing(a, idx, k, x, K, h, s);
                     }
+                    if constexpr (POLY) pj = emit_polyline(a, idx, pj, k, x, K, t, h, fma(s, h, t));
                     // dense output at the event (rk.py:715-738); k_t and t are not needed by the exit conversion
                     DenseWeights w;
                     dense_weights(s, w);
@@ -369,6 +407,7 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
                     exit_state<NK>(k, x, x0, k0, xo, ko);
                 }
                 store_ray<IN>(a, idx, xo, ko, final_status, n_attempt, n_accept);
+                if constexpr (POLY) a.poly_count[idx] = pj;
                 if constexpr (DISK) {
                     if (!disk_hit) a.disk_xy[2 * idx] = a.disk_xy[2 * idx + 1] = __longlong_as_double(0x7ff8000000000000LL);
                 }
@@ -392,6 +431,7 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
                         n_accept = 0;
                         rejected = false;
                         disk_hit = false;
+                        pj = 0;
                         t = 0.0;
                         if (!enters) {
                             state = MISSED_SPHERE;
@@ -453,6 +493,7 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
                                 }
                             }
                         }
+                        if constexpr (POLY) pj = emit_polyline(a, idx, pj, k, x, K, t, h, t_new);
                         h_abs *= factor;
                         t = t_new;
                         rejected = false;

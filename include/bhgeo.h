@@ -107,6 +107,15 @@ int bhg_trace_schwarzschild_f64(const double* in, const double* in_dir, double* 
 typedef struct bhg_extras {
     double disk_r_in, disk_r_out; /* same length unit as M; the disk is off unless disk_r_out > 0 and disk_xy != NULL */
     double* disk_xy;
+    /* Polyline: positions sampled at lambda_j = linspace(0, lambda_max, poly_n)[j] up to the termination time - what
+     * curvedpy returns for nr_points_curve (RelativisticRenderEngine.py:293-294,299-300) and what checkHitDisk scans
+     * (LimitedRelativisticRenderEngine.py:283-285).  poly_xyz: n x poly_n x 3 doubles (entries at and beyond
+     * poly_count[i] are left untouched), poly_count: n int32.  Off unless poly_n >= 2 and both pointers are set.
+     * Needs an explicit params->lambda_max > 0.  Parity mode, float64 AOS layout. */
+    int32_t poly_n;
+    int32_t reserved;
+    double* poly_xyz;
+    int32_t* poly_count;
 } bhg_extras;
 
 /* bhg_trace_schwarzschild_f64 / _host with extras (extras == NULL is identical to the plain call). */

@@ -143,7 +143,7 @@ def default_lambda_max(M, r_sphere):
 
 
 def trace_one(x0, k0, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, max_step=np.inf,
-              eps_horizon=0.01, lambda_max=None, return_sol=False, disk=None):
+              eps_horizon=0.01, lambda_max=None, return_sol=False, disk=None, polyline=None):
     """One ray through real scipy solve_ivp.  Returns dict(exit_pos, exit_dir, status, nfev, n_accept, lam)."""
     from scipy.integrate import solve_ivp
 
@@ -200,9 +200,31 @@ def trace_one(x0, k0, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, max_step=np.in
         plane_crossing.direction = 0
         events.append(plane_crossing)
 
+    t_eval = None
+    if polyline is not None:
+        # the reference asks for nr_points_curve samples on linspace(0, curve_end, N) (RelativisticRenderEngine.py:
+        # 293-294: nr_points_curve=10000) and gets the ones up to the termination time back
+        t_eval = np.linspace(0.0, lambda_max, int(polyline))
     with np.errstate(all="ignore"):
         res = solve_ivp(fun, (0.0, lambda_max), y0, method="RK45", events=events,
-                        rtol=rtol, atol=atol, max_step=max_step)
+                        rtol=rtol, atol=atol, max_step=max_step, t_eval=t_eval)
+    if polyline is not None:
+        pts = np.full((int(polyline), 3), np.nan)
+        cnt = res.y.shape[1] if res.y.ndim == 2 else 0
+        for j in range(cnt):
+            yj = res.y[:, j]
+            (X, Y, Z), _ = sph_to_xyz((yj[3], yj[5], yj[7]), (yj[2], yj[4], yj[6]))
+            pts[j] = (X, Y, Z)
+        out["poly_xyz"], out["poly_count"] = pts, cnt
+        # with t_eval, res.t / res.y hold the samples, not the terminal state: recover it from the events
+        if res.status == 1:
+            ev = 0 if len(res.t_events[0]) > 0 else 1
+            res_t_end, res_y_end = res.t_events[ev][-1], res.y_events[ev][-1]
+        else:
+            from scipy.integrate import solve_ivp as _s
+            r2 = _s(fun, (0.0, lambda_max), y0, method="RK45", events=events, rtol=rtol, atol=atol, max_step=max_step)
+            res_t_end, res_y_end = r2.t[-1], r2.y[:, -1]
+        res = _WithEnd(res, res_t_end, res_y_end)
     if disk is not None:
         r_in, r_out = disk
         for tc, yc in zip(res.t_events[-1], res.y_events[-1]):
@@ -234,8 +256,18 @@ def trace_one(x0, k0, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, max_step=np.in
     return out
 
 
+class _WithEnd:
+    """solve_ivp result whose .t / .y end with the terminal state (used when t_eval replaced them by samples)."""
+
+    def __init__(self, res, t_end, y_end):
+        self.__dict__.update(res)
+        self.t = np.array([0.0, t_end])
+        self.y = np.stack([res.y[:, 0] if res.y.size else y_end, y_end], axis=1)
+        self._n_accept = None
+
+
 def trace(entry_pos, entry_dir, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, max_step=np.inf,
-          eps_horizon=0.01, lambda_max=None, disk=None):
+          eps_horizon=0.01, lambda_max=None, disk=None, polyline=None):
     """Batched face of `trace_one` with the north-star signature (pure-Python loop; small N only)."""
     entry_pos = np.asarray(entry_pos, dtype=np.float64).reshape(-1, 3)
     entry_dir = np.asarray(entry_dir, dtype=np.float64).reshape(-1, 3)
@@ -246,15 +278,22 @@ def trace(entry_pos, entry_dir, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, max_
     nfev = np.empty(n, dtype=np.int32)
     n_accept = np.empty(n, dtype=np.int32)
     disk_xy = np.empty((n, 2))
+    poly = np.full((n, int(polyline), 3), np.nan) if polyline is not None else None
+    pcnt = np.zeros(n, dtype=np.int32)
     for i in range(n):
         o = trace_one(entry_pos[i], entry_dir[i], M, r_sphere, rtol, atol, max_step, eps_horizon, lambda_max,
-                      disk=disk)
+                      disk=disk, polyline=polyline)
         exit_pos[i], exit_dir[i], status[i] = o["exit_pos"], o["exit_dir"], o["status"]
         nfev[i], n_accept[i] = o["nfev"], o["n_accept"]
         disk_xy[i] = o["disk_xy"]
+        if polyline is not None and "poly_xyz" in o:
+            poly[i], pcnt[i] = o["poly_xyz"], o["poly_count"]
+    res = (exit_pos, exit_dir, status, nfev, n_accept)
     if disk is not None:
-        return exit_pos, exit_dir, status, nfev, n_accept, disk_xy
-    return exit_pos, exit_dir, status, nfev, n_accept
+        res += (disk_xy,)
+    if polyline is not None:
+        res += (poly, pcnt)
+    return res
 
 
 def _pool_worker(args):

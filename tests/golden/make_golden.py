@@ -27,8 +27,11 @@ def run(pos, d, procs=8, **kw):
     res = R.trace_pool(pos, d, procs, chunk=64, **kw)
     ep, ed, st, nfev, nacc = res[:5]
     out = dict(entry_pos=pos, entry_dir=d, exit_pos=ep, exit_dir=ed, status=st, nfev=nfev, n_accept=nacc)
-    if len(res) > 5:
-        out["disk_xy"] = res[5]
+    extra = list(res[5:])
+    if "disk" in kw and kw["disk"] is not None:
+        out["disk_xy"] = extra.pop(0)
+    if "polyline" in kw and kw["polyline"] is not None:
+        out["poly_xyz"], out["poly_count"] = extra.pop(0), extra.pop(0)
     return out
 
 
@@ -116,6 +119,17 @@ def main():
     p5, d5, _ = raygen.near_critical_bundle(192, in_plane=False, seed=11)
     gd = run(np.concatenate([pd_, p5]), np.concatenate([dd_, d5]), disk=(6.0, 20.0))
     save("disk_crossing.npz", gd, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, disk_r_in=6.0, disk_r_out=20.0)
+
+    # polyline samples on linspace(0, curve_end, K) (t_eval of solve_ivp; RelativisticRenderEngine.py:293-294):
+    # RRE call shape (no sphere, M = 0.5, curve_end = 50) and sphere contract (lambda_max = 200)
+    rot = raygen.look_at_rotation((12.0, -8.0, 4.0))
+    dr = raygen.camera_rays(8, 8, 1, 1.0, 1.0, rot, 42, "mt19937")
+    pr = np.tile([12.0, -8.0, 4.0], (dr.shape[0], 1))
+    save("polyline_rre.npz", run(pr, dr, M=0.5, r_sphere=np.inf, lambda_max=50.0, polyline=33), M=0.5, r_sphere=np.inf,
+         rtol=1e-3, atol=1e-6, lambda_max=50.0, polyline=33)
+    pp, dp = raygen.config_bundle(8, 8, 1, jitter="mt19937", fov=0.45)
+    save("polyline_sphere.npz", run(pp, dp, lambda_max=200.0, polyline=41), M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6,
+         lambda_max=200.0, polyline=41)
 
     # analytic known answers: deflection between sphere entry and exit
     bflat = np.array([5.3, 6.0, 8.0, 12.0, 20.0, 40.0])

@@ -30,6 +30,7 @@ def test_rre_call_shape_per_ray_and_batch():
         assert result["hit_blackhole"] == bool(g["status"][i] == 1)
         x, y, z = x_xyz
         kx, ky, kz = k_xyz
+        assert x_xyz.shape[1] > 2 and np.allclose(x_xyz[:, 0], g["entry_pos"][i])
         end_loc_i = np.array([x[-1], y[-1], z[-1]])
         end_dir_i = np.array([kx[-1], ky[-1], kz[-1]])
         assert np.abs(end_loc_i - g["exit_pos"][i]).max() / 50.0 < 1e-6
@@ -56,7 +57,28 @@ def test_lim_call_shape_scaling_and_messages():
     # per-ray shape and the 'Outside' message when the affine length runs out (LIM.py:308-314)
     x, y, z, el, ed, mes = sw.ray_trace(d[5], locs[5], ratio_obj_to_blackhole=ratio)
     assert mes["hit_blackhole"] == bool(o["status"][5] == 1) and "error" not in mes
-    assert np.allclose(el, end_loc[5]) and len(x) == 2
+    assert np.allclose(el, end_loc[5]) and len(x) > 10
+    # the polyline (r_s units) starts at the entry point, stays inside the sphere and ends at the exit point
+    rr = np.sqrt(x * x + y * y + z * z)
+    assert abs(rr[0] - ratio) < 1e-9 and abs(rr[-1] - ratio) < 1e-6 and (rr <= ratio + 1e-9).all()
+    # the reference's own checkHitDisk scan (LIM.py:413-438) applied to that polyline agrees with the in-flight event
+    def check_hit_disk(x, y, z, R_in, R_out):
+        for i in range(len(x) - 1):
+            if (z[i + 1] < 0 and z[i] >= 0) or (z[i + 1] > 0 and z[i] <= 0):
+                l0 = -z[i] / (z[i + 1] - z[i])
+                xd, yd = x[i] + (x[i + 1] - x[i]) * l0, y[i] + (y[i + 1] - y[i]) * l0
+                R = np.sqrt(xd ** 2 + yd ** 2)
+                if R_in <= R <= R_out:
+                    return np.array([xd, yd])
+        return None
+    res = sw.ray_trace_batch(d, locs, ratio_obj_to_blackhole=ratio, disk=(3.0, 12.0))
+    n_hit = 0
+    for i in np.nonzero(np.isfinite(res[-1][:, 0]))[0][:6]:
+        xi, yi, zi, *_ = sw.ray_trace(d[i], locs[i], ratio_obj_to_blackhole=ratio, nr_points_curve=2048)
+        h = check_hit_disk(xi, yi, zi, 3.0, 12.0)
+        assert h is not None and np.abs(h - res[-1][i]).max() < 0.05   # chord interpolation vs exact crossing
+        n_hit += 1
+    assert n_hit > 0
     x, y, z, el, ed, mes = sw.ray_trace(d[5], locs[5], ratio_obj_to_blackhole=ratio, curve_end=5.0)
     assert mes.get("error") == "Outside" and mes["hit_blackhole"] is False
 

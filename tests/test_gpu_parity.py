@@ -424,3 +424,28 @@ def test_flat_limit_and_concurrent_callers(api):
     for r in results:
         assert np.array_equal(r[2], g["status"])
         assert np.array_equal(r[0], results[0][0], equal_nan=True)
+
+
+@pytest.mark.parametrize("name", ["polyline_rre.npz", "polyline_sphere.npz"])
+def test_polyline_samples(api, name):
+    """SURVEY 8f row 2 (second half): positions on linspace(0, curve_end, K) up to termination, as solve_ivp's t_eval
+    returns them to the reference (RelativisticRenderEngine.py:293-294,299-300)."""
+    g = load_golden(name)
+    kw = golden_kwargs(g)
+    K = int(g["polyline"])
+    ep, ed, st, poly, cnt = api.trace(g["entry_pos"], g["entry_dir"], polyline=K, **kw)
+    assert np.array_equal(st, g["status"])
+    assert np.array_equal(cnt, g["poly_count"])
+    scale = 60.0 if np.isfinite(kw["r_sphere"]) else 50.0
+    for i in range(len(cnt)):
+        c = cnt[i]
+        assert np.abs(poly[i, :c] - g["poly_xyz"][i, :c]).max() / scale < 1e-6
+        assert np.isnan(poly[i, c:]).all()
+    # sample 0 is the entry point; without the option nothing else changes
+    assert np.abs(poly[:, 0] - g["entry_pos"]).max() < 1e-12
+    ep0, ed0, st0 = api.trace(g["entry_pos"], g["entry_dir"], **kw)
+    assert np.array_equal(ep0, ep, equal_nan=True) and np.array_equal(ed0, ed, equal_nan=True)
+    # together with the disk event
+    if np.isfinite(kw["r_sphere"]):
+        out = api.trace(g["entry_pos"], g["entry_dir"], polyline=K, disk=(6.0, 20.0), **kw)
+        assert np.array_equal(out[4], poly, equal_nan=True) and out[3].shape == (len(cnt), 2)
