@@ -88,6 +88,11 @@ _SIGNATURES = {
                                                  ctypes.POINTER(BhgParams), ctypes.c_int32]),
     "bhg_host_alloc": (_P, [ctypes.c_int64]),
     "bhg_host_free": (None, [_P]),
+    "bhg_device_alloc": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.POINTER(_P)]),
+    "bhg_device_free": (ctypes.c_int, [_P, ctypes.c_int32]),
+    "bhg_ipc_export": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_char_p]),
+    "bhg_ipc_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int32, ctypes.POINTER(_P)]),
+    "bhg_ipc_close": (ctypes.c_int, [_P, ctypes.c_int32]),
     "bhg_sum_counters": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int32, _P,
                                         ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
                                         ctypes.POINTER(ctypes.c_int64)]),

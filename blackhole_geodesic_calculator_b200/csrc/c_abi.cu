@@ -769,6 +769,56 @@ void bhg_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
+int bhg_device_alloc(int64_t bytes, int32_t device, void** ptr) {
+    if (!ptr || bytes <= 0) return fail(BHG_ERR_INVALID_ARGUMENT, "bhg_device_alloc: ptr NULL or bytes <= 0");
+    DeviceRestore restore_device_on_exit;
+    DeviceCtx* c;
+    int rc = ensure_device(device, &c);
+    if (rc) return rc;
+    // plain cudaMalloc (not the stream-ordered pool): legacy CUDA IPC can only export such allocations
+    BHG_CUDA(cudaMalloc(ptr, (size_t)bytes));
+    return 0;
+}
+
+int bhg_device_free(void* ptr, int32_t device) {
+    if (!ptr) return 0;
+    DeviceRestore restore_device_on_exit;
+    BHG_CUDA(cudaSetDevice(device));
+    BHG_CUDA(cudaFree(ptr));
+    return 0;
+}
+
+int bhg_ipc_export(const void* ptr, int32_t device, unsigned char handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "bhgeo.h documents a 64-byte handle");
+    if (!ptr || !handle) return fail(BHG_ERR_INVALID_ARGUMENT, "bhg_ipc_export: NULL argument");
+    DeviceRestore restore_device_on_exit;
+    BHG_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    BHG_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(ptr)));
+    memcpy(handle, &h, sizeof(h));
+    return 0;
+}
+
+int bhg_ipc_open(const unsigned char handle[64], int32_t device, void** ptr) {
+    if (!ptr || !handle) return fail(BHG_ERR_INVALID_ARGUMENT, "bhg_ipc_open: NULL argument");
+    DeviceRestore restore_device_on_exit;
+    DeviceCtx* c;
+    int rc = ensure_device(device, &c);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    BHG_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int bhg_ipc_close(void* ptr, int32_t device) {
+    if (!ptr) return 0;
+    DeviceRestore restore_device_on_exit;
+    BHG_CUDA(cudaSetDevice(device));
+    BHG_CUDA(cudaIpcCloseMemHandle(ptr));
+    return 0;
+}
+
 int bhg_sum_counters(const int32_t* counters_dev, const int32_t* status_dev, int64_t n, int32_t device, void* stream,
                      int64_t* n_attempt, int64_t* n_accept, int64_t* n_integrated) {
     DeviceRestore restore_device_on_exit;

@@ -198,6 +198,19 @@ int bhg_trace_camera_sky_host(const bhg_camera* cam, float* uv, int32_t* status,
 void* bhg_host_alloc(int64_t bytes);
 void bhg_host_free(void* p);
 
+/* Peer-mapped device memory for the multi-GPU frame gather (no reference counterpart: the reference is one
+ * process; its only parallelism is the offline mp.Pool camera pre-run, RelativisticRenderEngineCamEdition.py:216).
+ * The rank that owns a frame allocates its exit buffers with bhg_device_alloc, exports a 64-byte CUDA IPC handle,
+ * the other ranks (one process per GPU) open it and pass the mapped pointers as out / out_dir / status of
+ * bhg_trace_schwarzschild_f64 together with `order` = their ray indices: every GPU then stores its exit states
+ * straight into the owner's HBM over NVLink while it integrates, and no gather follows.
+ * bhg_ipc_open must be called from a different process than the exporter (CUDA restriction). */
+int bhg_device_alloc(int64_t bytes, int32_t device, void** ptr);
+int bhg_device_free(void* ptr, int32_t device);
+int bhg_ipc_export(const void* ptr, int32_t device, unsigned char handle[64]);
+int bhg_ipc_open(const unsigned char handle[64], int32_t device, void** ptr);
+int bhg_ipc_close(void* ptr, int32_t device);
+
 /* Totals of the last completed trace on `device` from the calling thread's point of view: sum of RK45
  * attempts and of RHS evaluations (nfev = 2 + 6 attempts per integrated ray) — used for roofline
  * accounting.  Only valid if the trace was given a `counters` buffer; otherwise returns zeros. */

@@ -1,0 +1,86 @@
+"""Strong scaling of ONE frame (configs[1]: 5,242,880 rays) over the ranks of a torchrun launch, gather included.
+
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 \
+      scripts/strong_frame.py
+
+Every rank holds the full entry buffers (as a Blender process per GPU would after generating the camera rays),
+integrates its interleaved shard and the exit buffers are gathered on rank 0 (distributed.trace_sharded).
+Prints, for chunks in (1, 2, 4, 8), the frame latency (CUDA events on rank 0, max over ranks) so the overlap of
+the gather with the integration can be read directly.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from blackhole_geodesic_calculator_b200 import api, distributed as D, raygen  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cam = api.make_camera(raygen.CFG_CAMERA_POS, raygen.look_at_rotation(raygen.CFG_CAMERA_POS), 1280, 1024,
+                          raygen.CFG_FOV, raygen.CFG_FOV, seed=raygen.CFG_SEED, jitter="philox")
+    pos, d, _ = api.generate_rays(cam, 4 * 1280 * 1024, raygen.CFG_R_SPHERE, device=local)   # device generator, same on all ranks
+    kw = dict(M=raygen.CFG_M, r_sphere=raygen.CFG_R_SPHERE, rtol=1e-3, atol=1e-6)
+    res = {}
+    for chunks in (1, 2, 4, 8):
+        times = []
+        for it in range(8):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = D.trace_sharded(pos, d, chunks=chunks, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if it >= 3:
+                times.append(float(t))
+        res[chunks] = float(np.median(times))
+    # peer-memory route: exit states stored straight into rank 0's HBM by every GPU's trace kernel
+    frame = D.PeerFrame(pos.shape[0], owner=0)
+    peer = {}
+    for width in (0, 1280):
+        times = []
+        for it in range(10):
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            pout = D.trace_sharded_peer(pos, d, frame, image_width=width, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if it >= 3:
+                times.append(float(t))
+        peer[width] = float(np.median(times))
+    same = None
+    if rank == 0:
+        same = all(torch.equal(a, b) for a, b in zip(pout, out))
+    frame.close()
+    if rank == 0:
+        n = pos.shape[0]
+        st = out[2]
+        print(json.dumps({"n_gpus": world, "rays": n, "gather_frame_ms_by_chunks": res, "peer_frame_ms_by_image_width": peer,
+                          "peer_equals_gather": same, "best_rays_per_s": n / (min(peer.values()) * 1e-3),
+                          "status_counts": torch.bincount(st.to(torch.int64), minlength=6).tolist()}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -39,7 +39,7 @@ def _worker(rank, world, port, n, q):
 
         pos, d = raygen.config_bundle(32, 32, 1)
         pos, d = pos[:n], d[:n]
-        out = D.trace_sharded(pos, d, dst=0, tracer=tracer, rtol=1e-3, atol=1e-6)
+        out = D.trace_sharded(pos, d, dst=0, tracer=tracer, chunks=3, rtol=1e-3, atol=1e-6)
         if rank == 0:
             ref = tracer(pos, d, rtol=1e-3, atol=1e-6)
             ok = all(np.array_equal(a, b, equal_nan=True) for a, b in zip(out, ref))
@@ -64,3 +64,16 @@ def test_trace_sharded_world2_gloo(n):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [("none", 0), ("ok", n)]
+
+
+@pytest.mark.parametrize("n,world,width", [(8 * 48 * 5, 2, 48), (1000, 3, 0), (8 * 48 * 5, 8, 48), (31, 4, 0)])
+def test_shard_order_partitions_the_frame(n, world, width):
+    """Every ray belongs to exactly one rank; shards differ by at most one 32-slot group."""
+    parts = [D.shard_order(n, r, world, width) for r in range(world)]
+    assert all(p.dtype == np.int32 for p in parts)
+    assert sorted(np.concatenate(parts).tolist()) == list(range(n))
+    sizes = [len(p) for p in parts]
+    assert max(sizes) - min(sizes) <= 32
+    if width:   # a group of 32 slots is a 4 x 8 pixel tile
+        y, x = np.divmod(parts[0][:32].astype(np.int64), width)
+        assert x.max() - x.min() == 3 and y.max() - y.min() == 7

@@ -102,7 +102,8 @@ def test_cam_call_shape():
 
 
 def test_trace_sharded_nccl_two_gpus():
-    """Interleaved sharding + NCCL gather on real devices (needs >= 2 GPUs; the gloo twin runs on CPU)."""
+    """Interleaved sharding + NCCL gather, and the peer-memory frame (CUDA IPC over NVLink), on real devices
+    (needs >= 2 GPUs; the gloo twin of the gather runs on CPU)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -136,11 +137,19 @@ def _nccl_worker(rank, world, port, q):
         tp = torch.from_numpy(pos).cuda()
         td = torch.from_numpy(d).cuda()
         out = distributed.trace_sharded(tp, td, dst=0)
-        if rank == 0:
-            ref = api.trace(tp, td)
-            ok = all(torch.equal(a, b) for a, b in zip(out, ref))
-            q.put("ok" if ok else "mismatch")
-        else:
-            q.put("none" if out is None else "unexpected")
+        # same frame through the peer-memory route: both GPUs store into rank 0's HBM, no gather
+        frame = distributed.PeerFrame(tp.shape[0], owner=0)
+        try:
+            peer = [distributed.trace_sharded_peer(tp, td, frame, image_width=w) for w in (0, 64)]
+            torch.cuda.synchronize()
+            if rank == 0:
+                ref = api.trace(tp, td)
+                ok = all(torch.equal(a, b) for a, b in zip(out, ref))
+                ok = ok and all(torch.equal(a, b) for pr in peer for a, b in zip(pr, ref))
+                q.put("ok" if ok else "mismatch")
+            else:
+                q.put("none" if out is None and peer == [None, None] else "unexpected")
+        finally:
+            frame.close()
     finally:
         dist.destroy_process_group()
