@@ -93,6 +93,8 @@ _SIGNATURES = {
     "bhg_ipc_export": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_char_p]),
     "bhg_ipc_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int32, ctypes.POINTER(_P)]),
     "bhg_ipc_close": (ctypes.c_int, [_P, ctypes.c_int32]),
+    "bhg_copy_rows": (ctypes.c_int, [_P, ctypes.c_int64, _P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                     ctypes.c_int32, _P]),
     "bhg_sum_counters": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_int32, _P,
                                         ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64),
                                         ctypes.POINTER(ctypes.c_int64)]),

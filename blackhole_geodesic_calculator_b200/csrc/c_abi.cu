@@ -819,6 +819,18 @@ int bhg_ipc_close(void* ptr, int32_t device) {
     return 0;
 }
 
+int bhg_copy_rows(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t row_bytes, int64_t rows,
+                  int32_t device, void* stream) {
+    if (rows <= 0 || row_bytes <= 0) return 0;
+    if (!dst || !src || dst_pitch < row_bytes || src_pitch < row_bytes)
+        return fail(BHG_ERR_INVALID_ARGUMENT, "bhg_copy_rows: NULL pointer or pitch < row_bytes");
+    DeviceRestore restore_device_on_exit;
+    BHG_CUDA(cudaSetDevice(device));
+    BHG_CUDA(cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)row_bytes, (size_t)rows,
+                               cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
 int bhg_sum_counters(const int32_t* counters_dev, const int32_t* status_dev, int64_t n, int32_t device, void* stream,
                      int64_t* n_attempt, int64_t* n_accept, int64_t* n_integrated) {
     DeviceRestore restore_device_on_exit;

@@ -202,6 +202,21 @@ class PeerFrame:
             self._order_cache[key] = torch.from_numpy(o).to(torch.device("cuda", self.device))
         return self._order_cache[key]
 
+    def copy_plan(self, image_width=0):
+        """Cached band-cyclic shard of this rank: compact local in/out buffers, side stream."""
+        import torch
+
+        key = ("copy", int(image_width))
+        if key not in self._order_cache:
+            band, mine, m, tiles_ok = band_plan(self.n, self.rank, self.world, int(image_width))
+            dev = torch.device("cuda", self.device)
+            f64 = lambda: torch.empty((m, 3), dtype=torch.float64, device=dev)
+            self._order_cache[key] = dict(
+                band=band, m=m, tiles_ok=tiles_ok, in_pos=f64(), in_dir=f64(),
+                out_pos=f64(), out_dir=f64(), status=torch.empty(m, dtype=torch.int32, device=dev),
+                side=torch.cuda.Stream(dev))
+        return self._order_cache[key]
+
     def fence(self):
         """Stream-ordered all-ranks fence (1-element all-reduce; no host synchronisation)."""
         import torch.distributed as dist
@@ -225,29 +240,100 @@ class PeerFrame:
         self._base = None
 
 
-def trace_sharded_peer(entry_pos, entry_dir, frame: PeerFrame, *, image_width=0, fence_before=True, **trace_kw):
-    """Trace one frame across all ranks with the exit states written directly into `frame` (the owner's HBM).
+def band_plan(n: int, rank: int, world: int, image_width: int = 0, band: int = 8192):
+    """Band-cyclic partition for the copy route: the frame is cut into bands of `band` consecutive rays (8 image rows
+    when `image_width` is a usable tile hint), band b belongs to rank b mod world.  Returns (band, local band ids,
+    local ray count, tiles_ok)."""
+    tiles_ok = image_width > 0 and image_width % 4 == 0 and n % (8 * image_width) == 0
+    if tiles_ok:
+        band = 8 * image_width
+    nb = (n + band - 1) // band
+    mine = np.arange(rank, nb, world, dtype=np.int64)
+    m = int(sum(min(band, n - int(b) * band) for b in mine))
+    return band, mine, m, tiles_ok
+
+
+def trace_sharded_peer(entry_pos, entry_dir, frame: PeerFrame, *, image_width=0, fence_before=True, route="auto",
+                       chunks=2, **trace_kw):
+    """Trace one frame across all ranks and deliver the exit states into `frame` (the owner's HBM) without a gather.
 
     entry_pos / entry_dir: the frame's full [n,3] float64 CUDA tensors, present on every rank (each rank generates
-    them from the camera).  Each rank integrates the rays of `frame.order(image_width)` and stores their exit
-    states at their final position in the owner's buffers through the NVLink mapping - the kernel is the same
-    bhg_trace_schwarzschild_f64 with remote out pointers and an `order` array.  A closing 1-element all-reduce
-    orders the owner's stream after every rank's kernel; `fence_before` adds the same fence ahead of the kernel so
-    that the previous frame's consumer on the owner has finished with the buffers before anyone overwrites them.
+    them from the camera).  Two routes, same results:
+      "copy"   band-cyclic shards (band_plan): each rank integrates its bands into compact local buffers in `chunks`
+               pieces and a side stream deals every finished piece into the owner's buffers with strided
+               copy-engine copies over NVLink (bhg_copy_rows) while the next piece integrates;
+      "stores" 32-ray groups dealt round-robin (shard_order): the trace kernel itself stores each exit state at its
+               final position in the owner's memory through the mapping (remote `out` pointers + `order`).  No
+               second pass at all, but 24-byte remote stores: best at 2 GPUs, ingress-bound at 8
+               (profiles/r1q_strong_frame_n8.json);
+      "auto"   "stores" up to 2 ranks, "copy" beyond.
+    A closing 1-element all-reduce orders the owner's stream after every rank's work; `fence_before` adds the same
+    fence ahead so the owner's consumer of the previous frame has finished before anyone overwrites the buffers.
     Returns the owner's (exit_pos, exit_dir, status) views, None elsewhere.  Asynchronous on the current stream."""
     import torch
     from . import api
 
     if entry_pos.shape[0] != frame.n:
         raise ValueError("trace_sharded_peer: frame was built for a different ray count")
+    if route == "auto":
+        route = "stores" if frame.world <= 2 else "copy"
+    if route not in ("copy", "stores"):
+        raise ValueError("route must be 'auto', 'copy' or 'stores'")
     dev = entry_pos.device
-    order = frame.order(image_width)
-    params = api.make_params(**trace_kw)
+    cur = torch.cuda.current_stream(dev)
+    if route == "stores":
+        order = frame.order(image_width)
+        params = api.make_params(**trace_kw)
+        if fence_before:
+            frame.fence()
+        if order.numel():
+            api.trace_device(entry_pos.data_ptr(), entry_dir.data_ptr(), frame.pos_ptr, frame.dir_ptr,
+                             frame.status_ptr, None, order.data_ptr(), order.numel(), api.LAYOUT_AOS, params,
+                             device=dev.index, stream=cur.cuda_stream)
+        frame.fence()
+        return frame.tensors()
+
+    plan = frame.copy_plan(image_width)
+    band, m, W, r = plan["band"], plan["m"], frame.world, frame.rank
+    params = api.make_params(image_width=image_width if plan["tiles_ok"] else 0, **trace_kw)
     if fence_before:
         frame.fence()
-    if order.numel():
-        api.trace_device(entry_pos.data_ptr(), entry_dir.data_ptr(), frame.pos_ptr, frame.dir_ptr, frame.status_ptr,
-                         None, order.data_ptr(), order.numel(), api.LAYOUT_AOS, params, device=dev.index,
-                         stream=torch.cuda.current_stream(dev).cuda_stream)
+    if m:
+        side, lib = plan["side"], frame._lib
+        nb_local = (m + band - 1) // band
+        # compact this rank's bands (copy engine, strided source); the frame's last band may be partial
+        full_all, tail_all = m // band, m % band
+        for src, dst in ((entry_pos, plan["in_pos"]), (entry_dir, plan["in_dir"])):
+            frame._check(lib.bhg_copy_rows(dst.data_ptr(), band * 24, src.data_ptr() + r * band * 24, W * band * 24,
+                                           band * 24, full_all, dev.index, cur.cuda_stream))
+            if tail_all:
+                frame._check(lib.bhg_copy_rows(dst.data_ptr() + full_all * band * 24, tail_all * 24,
+                                               src.data_ptr() + (r + full_all * W) * band * 24, tail_all * 24,
+                                               tail_all * 24, 1, dev.index, cur.cuda_stream))
+        # pieces shrink towards the end (each half of what is left) so the last, exposed copy is short
+        pieces = max(1, min(int(chunks), nb_local))
+        cuts = [0] + [max(1, round(nb_local * (1.0 - 0.5 ** (c + 1)))) for c in range(pieces - 1)] + [nb_local]
+        cuts = sorted(set(cuts))
+        for b0, b1 in zip(cuts[:-1], cuts[1:]):
+            lo, hi = b0 * band, min(b1 * band, m)
+            api.trace_device(plan["in_pos"].data_ptr() + lo * 24, plan["in_dir"].data_ptr() + lo * 24,
+                             plan["out_pos"].data_ptr() + lo * 24, plan["out_dir"].data_ptr() + lo * 24,
+                             plan["status"].data_ptr() + lo * 4, None, None, hi - lo, api.LAYOUT_AOS, params,
+                             device=dev.index, stream=cur.cuda_stream)
+            done = torch.cuda.Event()
+            done.record(cur)
+            side.wait_event(done)
+            full, tail = (hi - lo) // band, (hi - lo) % band
+            first_global = r + b0 * W               # local band j is global band r + j * W
+            for dst, src, width in ((frame.pos_ptr, plan["out_pos"].data_ptr(), 24),
+                                    (frame.dir_ptr, plan["out_dir"].data_ptr(), 24),
+                                    (frame.status_ptr, plan["status"].data_ptr(), 4)):
+                frame._check(lib.bhg_copy_rows(dst + first_global * band * width, W * band * width, src + lo * width,
+                                               band * width, band * width, full, dev.index, side.cuda_stream))
+                if tail:
+                    frame._check(lib.bhg_copy_rows(dst + (first_global + full * W) * band * width, tail * width,
+                                                   src + (lo + full * band) * width, tail * width, tail * width, 1,
+                                                   dev.index, side.cuda_stream))
+        cur.wait_stream(side)
     frame.fence()
     return frame.tensors()

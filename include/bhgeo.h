@@ -210,6 +210,11 @@ int bhg_device_free(void* ptr, int32_t device);
 int bhg_ipc_export(const void* ptr, int32_t device, unsigned char handle[64]);
 int bhg_ipc_open(const unsigned char handle[64], int32_t device, void** ptr);
 int bhg_ipc_close(void* ptr, int32_t device);
+/* Asynchronous strided copy on `stream` (cudaMemcpy2DAsync, device to device, copy engine): `rows` rows of
+ * `row_bytes`, source pitch `src_pitch`, destination pitch `dst_pitch`; dst may be a bhg_ipc_open mapping.  Used to
+ * deal a rank's bands of exit states into the frame owner's buffers while the next piece is still integrating. */
+int bhg_copy_rows(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t row_bytes, int64_t rows,
+                  int32_t device, void* stream);
 
 /* Totals of the last completed trace on `device` from the calling thread's point of view: sum of RK45
  * attempts and of RHS evaluations (nfev = 2 + 6 attempts per integrated ray) — used for roofline

@@ -51,7 +51,8 @@ def main():
     # peer-memory route: exit states stored straight into rank 0's HBM by every GPU's trace kernel
     frame = D.PeerFrame(pos.shape[0], owner=0)
     peer = {}
-    for width in (0, 1280):
+    for route, width, chunks in (("stores", 0, 1), ("stores", 1280, 1), ("copy", 0, 1), ("copy", 1280, 1),
+                                 ("copy", 1280, 2), ("copy", 1280, 4), ("copy", 1280, 8)):
         times = []
         for it in range(10):
             if world > 1:
@@ -59,7 +60,7 @@ def main():
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            pout = D.trace_sharded_peer(pos, d, frame, image_width=width, **kw)
+            pout = D.trace_sharded_peer(pos, d, frame, image_width=width, route=route, chunks=chunks, **kw)
             e1.record()
             torch.cuda.synchronize()
             t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -67,7 +68,7 @@ def main():
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
             if it >= 3:
                 times.append(float(t))
-        peer[width] = float(np.median(times))
+        peer[f"{route}/w{width}/c{chunks}"] = float(np.median(times))
     same = None
     if rank == 0:
         same = all(torch.equal(a, b) for a, b in zip(pout, out))
@@ -75,7 +76,7 @@ def main():
     if rank == 0:
         n = pos.shape[0]
         st = out[2]
-        print(json.dumps({"n_gpus": world, "rays": n, "gather_frame_ms_by_chunks": res, "peer_frame_ms_by_image_width": peer,
+        print(json.dumps({"n_gpus": world, "rays": n, "gather_frame_ms_by_chunks": res, "peer_frame_ms": peer,
                           "peer_equals_gather": same, "best_rays_per_s": n / (min(peer.values()) * 1e-3),
                           "status_counts": torch.bincount(st.to(torch.int64), minlength=6).tolist()}))
     if world > 1:

@@ -77,3 +77,18 @@ def test_shard_order_partitions_the_frame(n, world, width):
     if width:   # a group of 32 slots is a 4 x 8 pixel tile
         y, x = np.divmod(parts[0][:32].astype(np.int64), width)
         assert x.max() - x.min() == 3 and y.max() - y.min() == 7
+
+
+@pytest.mark.parametrize("n,world,width", [(8 * 48 * 5, 2, 48), (20000, 3, 0), (8 * 48 * 5, 8, 48), (31, 4, 0),
+                                           (8192 * 3 + 5, 2, 0)])
+def test_band_plan_partitions_the_frame(n, world, width):
+    """Copy route: whole bands per rank, every ray exactly once, tile hint only when every band is 8 full rows."""
+    seen = []
+    for r in range(world):
+        band, mine, m, tiles_ok = D.band_plan(n, r, world, width)
+        idx = (mine[:, None] * band + np.arange(band)[None, :]).reshape(-1)
+        idx = idx[idx < n]
+        assert idx.size == m and (mine % world == r).all()
+        assert tiles_ok == bool(width) and (not tiles_ok or band == 8 * width)
+        seen += idx.tolist()
+    assert sorted(seen) == list(range(n))

@@ -140,15 +140,30 @@ def _nccl_worker(rank, world, port, q):
         # same frame through the peer-memory route: both GPUs store into rank 0's HBM, no gather
         frame = distributed.PeerFrame(tp.shape[0], owner=0)
         try:
-            peer = [distributed.trace_sharded_peer(tp, td, frame, image_width=w) for w in (0, 64)]
+            peer = []
+            for route, w, chunks in (("stores", 0, 1), ("stores", 64, 1), ("copy", 0, 1), ("copy", 64, 3)):
+                res = distributed.trace_sharded_peer(tp, td, frame, image_width=w, route=route, chunks=chunks)
+                peer.append(None if res is None else [t.clone() for t in res])
             torch.cuda.synchronize()
+            # ragged frame: the last band is partial and 3 pieces do not divide the bands
+            m = 3 * 8192 + 77
+            tp2, td2 = tp.repeat(8, 1)[:m].contiguous(), td.repeat(8, 1)[:m].contiguous()
+            frame2 = distributed.PeerFrame(m, owner=0)
+            try:
+                res2 = distributed.trace_sharded_peer(tp2, td2, frame2, route="copy", chunks=3)
+                torch.cuda.synchronize()
+                ok2 = True
+                if rank == 0:
+                    ok2 = all(torch.equal(a, b) for a, b in zip(res2, api.trace(tp2, td2)))
+            finally:
+                frame2.close()
             if rank == 0:
                 ref = api.trace(tp, td)
                 ok = all(torch.equal(a, b) for a, b in zip(out, ref))
-                ok = ok and all(torch.equal(a, b) for pr in peer for a, b in zip(pr, ref))
+                ok = ok and ok2 and all(torch.equal(a, b) for pr in peer for a, b in zip(pr, ref))
                 q.put("ok" if ok else "mismatch")
             else:
-                q.put("none" if out is None and peer == [None, None] else "unexpected")
+                q.put("none" if out is None and peer == [None] * 4 else "unexpected")
         finally:
             frame.close()
     finally:
