@@ -182,11 +182,11 @@ def run_b200(args):
     n = W * H * SPP
     pos_h, dir_h = frame_rays(rank)  # frame index = rank: frames shard across GPUs
     # pinned host buffers for the end-to-end leg
-    pin_pos, pin_dir = api.pinned_empty((n, 3)), api.pinned_empty((n, 3))
+    pin_pos, pin_dir = api.pinned_empty((n, 3), device=local), api.pinned_empty((n, 3), device=local)
     pin_pos[:] = pos_h
     pin_dir[:] = dir_h
-    pin_op, pin_od = api.pinned_empty((n, 3)), api.pinned_empty((n, 3))
-    pin_st = api.pinned_empty((n,), np.int32)
+    pin_op, pin_od = api.pinned_empty((n, 3), device=local), api.pinned_empty((n, 3), device=local)
+    pin_st = api.pinned_empty((n,), np.int32, device=local)
     pos = torch.from_numpy(pos_h).to(dev)
     d = torch.from_numpy(dir_h).to(dev)
     exit_pos, exit_dir = torch.empty_like(pos), torch.empty_like(pos)
@@ -289,7 +289,7 @@ def run_b200(args):
         cam_times.append(time.perf_counter() - t0)
 
     # (c) camera -> sky-lookup coordinates (next-row 3): 12 B/ray come back
-    pin_uv = api.pinned_empty((n, 2), np.float32)
+    pin_uv = api.pinned_empty((n, 2), np.float32, device=local)
     api.trace_camera_sky(cam, n, mode=args.mode, refill_threshold=args.threshold, device=local, buffers=(pin_uv, pin_st))
     barrier()
     t0 = time.perf_counter()
@@ -300,10 +300,10 @@ def run_b200(args):
     cam_times.append(time.perf_counter() - t0)
 
     # (d) the same host-buffer contract with float32 arrays (Blender's native precision): 28 B/ray over PCIe
-    f_pos, f_dir = api.pinned_empty((n, 3), np.float32), api.pinned_empty((n, 3), np.float32)
+    f_pos, f_dir = api.pinned_empty((n, 3), np.float32, device=local), api.pinned_empty((n, 3), np.float32, device=local)
     f_pos[:] = pos_h
     f_dir[:] = dir_h
-    f_out = (api.pinned_empty((n, 3), np.float32), api.pinned_empty((n, 3), np.float32), pin_st)
+    f_out = (api.pinned_empty((n, 3), np.float32, device=local), api.pinned_empty((n, 3), np.float32, device=local), pin_st)
     kw32 = dict(mode=args.mode, refill_threshold=args.threshold, image_width=0 if args.no_tiles else W, device=local,
                 out=f_out)
     api.trace_f32(f_pos, f_dir, **kw32)

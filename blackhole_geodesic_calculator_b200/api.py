@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 
 import numpy as np
 
@@ -284,13 +285,58 @@ def sum_counters(counters_ptr, status_ptr, n, device=0, stream=0):
     return a.value, b.value, c.value
 
 
-def pinned_empty(shape, dtype=np.float64):
-    """numpy array backed by page-locked host memory (fast, asynchronous staging in the host entry point)."""
+def device_numa_cpus(device=0):
+    """CPUs of the NUMA node the GPU's PCIe root hangs off (sysfs), or None when the platform does not say."""
+    lib = _lib.load()
+    buf = ctypes.create_string_buffer(32)
+    _lib.check(lib.bhg_device_pci_bus_id(int(device), buf, 32))
+    try:
+        with open(f"/sys/bus/pci/devices/{buf.value.decode().lower()}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+    except (OSError, ValueError):
+        return None
+    cpus = set()
+    for part in spec.split(","):
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus or None
+
+
+class _near_device:
+    """Temporarily run the calling thread on the GPU's NUMA node so first-touch places new pages there."""
+
+    def __init__(self, device):
+        self.device, self.prev = device, None
+
+    def __enter__(self):
+        if self.device is None or not hasattr(os, "sched_setaffinity") or os.environ.get("BHG_NUMA_BIND") == "0":
+            return self
+        cpus = device_numa_cpus(self.device)
+        allowed = os.sched_getaffinity(0)
+        if cpus and (cpus & allowed):
+            self.prev = allowed
+            os.sched_setaffinity(0, cpus & allowed)
+        return self
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            os.sched_setaffinity(0, self.prev)
+        return False
+
+
+def pinned_empty(shape, dtype=np.float64, device=None):
+    """numpy array backed by page-locked host memory (fast, asynchronous staging in the host entry point).
+    With `device`, the pages are placed on the NUMA node of that GPU (matters when several ranks share a host)."""
     lib = _lib.load()
     dtype = np.dtype(dtype)
     count = int(np.prod(shape))
     nbytes = max(count * dtype.itemsize, 1)
-    ptr = lib.bhg_host_alloc(nbytes)
+    with _near_device(device):
+        ptr = lib.bhg_host_alloc(nbytes)   # cudaHostAlloc populates and pins the pages here, on this node
     if not ptr:
         raise MemoryError("bhg_host_alloc failed: " + lib.bhg_last_error_string().decode())
     buf = (ctypes.c_char * nbytes).from_address(ptr)

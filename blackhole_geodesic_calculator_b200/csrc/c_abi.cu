@@ -831,6 +831,12 @@ int bhg_copy_rows(void* dst, int64_t dst_pitch, const void* src, int64_t src_pit
     return 0;
 }
 
+int bhg_device_pci_bus_id(int32_t device, char* buf, int32_t len) {
+    if (!buf || len < 16) return fail(BHG_ERR_INVALID_ARGUMENT, "bhg_device_pci_bus_id: buf NULL or len < 16");
+    BHG_CUDA(cudaDeviceGetPCIBusId(buf, len, device));
+    return 0;
+}
+
 int bhg_sum_counters(const int32_t* counters_dev, const int32_t* status_dev, int64_t n, int32_t device, void* stream,
                      int64_t* n_attempt, int64_t* n_accept, int64_t* n_integrated) {
     DeviceRestore restore_device_on_exit;

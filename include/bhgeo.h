@@ -216,6 +216,10 @@ int bhg_ipc_close(void* ptr, int32_t device);
 int bhg_copy_rows(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t row_bytes, int64_t rows,
                   int32_t device, void* stream);
 
+/* PCI bus id of `device` ("0000:1b:00.0"), so that a host process can place its pinned frame buffers on the NUMA
+ * node the GPU hangs off (api.pinned_empty(..., device=)); buf needs >= 16 bytes. */
+int bhg_device_pci_bus_id(int32_t device, char* buf, int32_t len);
+
 /* Totals of the last completed trace on `device` from the calling thread's point of view: sum of RK45
  * attempts and of RHS evaluations (nfev = 2 + 6 attempts per integrated ray) — used for roofline
  * accounting.  Only valid if the trace was given a `counters` buffer; otherwise returns zeros. */
