@@ -65,6 +65,7 @@ public:
             memcpy(dst, src, bytes);
             return;
         }
+        std::lock_guard<std::mutex> one_copy_at_a_time(call_mu_);  // host threads of different devices share the pool
         std::unique_lock<std::mutex> lk(mu_);
         const size_t parts = workers_.size() + 1;
         const size_t slice = ((bytes / parts) + 4095) & ~size_t(4095);
@@ -105,7 +106,7 @@ private:
             if (--pending_ == 0) done_.notify_one();
         }
     }
-    std::mutex mu_;
+    std::mutex call_mu_, mu_;
     std::condition_variable cv_, done_;
     std::vector<std::thread> workers_;
     char* dst_ = nullptr;
@@ -344,6 +345,16 @@ int ensure_stage(DeviceCtx* c, size_t need) {
     return 0;
 }
 
+// The host entry points queue asynchronous copies into the caller's arrays; on an early error return those must
+// not still be in flight when the caller gets its buffers back.
+struct DrainStreamsOnExit {
+    DeviceCtx* c;
+    ~DrainStreamsOnExit() {
+        for (auto& s : c->streams)
+            if (s) cudaStreamSynchronize(s);
+    }
+};
+
 }  // namespace
 
 extern "C" {
@@ -456,6 +467,7 @@ int bhg_trace_schwarzschild_f64_host_ex(const double* entry_pos, const double* e
     }
     const size_t need = 4 * vec + (size_t)n * 3 * sizeof(int32_t) + (disk ? (size_t)n * 16 : 0) + 1024;
     if ((rc = ensure_stage(c, need))) return rc;
+    DrainStreamsOnExit drain_streams_on_exit{c};
     char* base = (char*)c->stage;
     double* d_disk = (double*)(base + 4 * vec + (((size_t)n * 3 * sizeof(int32_t) + 15) / 16) * 16);
     double* d_pin = (double*)base;
@@ -591,6 +603,7 @@ int bhg_trace_schwarzschild_f32io_host(const float* entry_pos, const float* entr
     std::lock_guard<std::mutex> lk(c->host_mu);
     const size_t vec = (size_t)n * 3 * sizeof(float);
     if ((rc = ensure_stage(c, 4 * vec + (size_t)n * sizeof(int32_t) + 1024))) return rc;
+    DrainStreamsOnExit drain_streams_on_exit{c};
     char* base = (char*)c->stage;
     float* d_pin = (float*)base;
     float* d_din = (float*)(base + vec);
@@ -665,6 +678,7 @@ int bhg_trace_camera_f64_host(const bhg_camera* cam, double* exit_pos, double* e
     std::lock_guard<std::mutex> lk(c->host_mu);
     const size_t vec = (size_t)n * 3 * sizeof(double);
     if ((rc = ensure_stage(c, 4 * vec + (size_t)n * 3 * sizeof(int32_t) + 1024))) return rc;
+    DrainStreamsOnExit drain_streams_on_exit{c};
     char* base = (char*)c->stage;
     double* d_pin = (double*)base;
     double* d_din = (double*)(base + vec);
@@ -726,6 +740,7 @@ int bhg_trace_camera_sky_host(const bhg_camera* cam, float* uv, int32_t* status,
     std::lock_guard<std::mutex> lk(c->host_mu);
     const size_t vec = (size_t)n * 3 * sizeof(double);
     if ((rc = ensure_stage(c, 3 * vec + (size_t)n * (8 + 4) + 1024))) return rc;
+    DrainStreamsOnExit drain_streams_on_exit{c};
     char* base = (char*)c->stage;
     double* d_pin = (double*)base;
     double* d_din = (double*)(base + vec);
