@@ -110,3 +110,38 @@ def test_camera_validation_needs_no_gpu():
     assert rc == -1 and b"width/height" in lib.bhg_last_error_string()
     with pytest.raises(ValueError):
         api.make_camera((1, 2, 3), np.eye(3), 8, 8, jitter="mt19937")
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/bhgeo.h compiles as C99 and a C program can link the library and call it (the boundary is a C ABI,
+    not a Python extension): defaults, struct sizes, and an argument error reported through the C error string."""
+    import shutil
+    import subprocess
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no C compiler")
+    src = tmp_path / "use_bhgeo.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <string.h>
+#include "bhgeo.h"
+int main(void) {
+    bhg_params p;
+    bhg_default_params(&p);
+    if (sizeof(bhg_params) != 72 || p.M != 1.0 || p.r_sphere != 60.0 || p.rtol != 1e-3 || p.atol != 1e-6) return 1;
+    p.rtol = -1.0;
+    double buf[3] = {0, 0, 0};
+    int status = 0;
+    int rc = bhg_trace_schwarzschild_f64_host(buf, buf, buf, buf, &status, NULL, 1, &p, 0);
+    if (rc != BHG_ERR_INVALID_ARGUMENT || !strstr(bhg_last_error_string(), "rtol")) return 2;
+    printf("version %d\n", bhg_version());
+    return 0;
+}
+''')
+    exe = tmp_path / "use_bhgeo"
+    libdir = os.path.dirname(os.path.abspath(_lib.LIB_PATH))
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-lbhgeo", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert out.stdout.startswith("version ")
