@@ -11,7 +11,7 @@ from blackhole_geodesic_calculator_b200 import api, raygen  # noqa: E402
 from oracle import port, schwarzschild_ref as ref  # noqa: E402
 
 pos, d = raygen.config_bundle(1024, 1024, 5, jitter="philox")
-sel = np.arange(0, pos.shape[0], 16)
+sel = np.arange(0, pos.shape[0], int(sys.argv[1]) if len(sys.argv) > 1 else 16)
 p, q = np.ascontiguousarray(pos[sel]), np.ascontiguousarray(d[sel])
 ep, ed, st, cnt = api.trace(p, q, return_counters=True)
 o = port.trace(p, q)

@@ -151,7 +151,7 @@ def test_analytic_deflection_parity_mode(api):
 
 def test_full_frame_properties_and_subsample_parity(api):
     """BASELINE config 2 (1024 x 1024 x 5 spp = 5 242 880 rays) at full size: size-independent properties on
-    every ray, and per-ray parity against the oracle's C restatement on every 16th ray (327 680 rays)."""
+    every ray, and per-ray parity against the oracle's C restatement on EVERY ray."""
     import torch
     from blackhole_geodesic_calculator_b200 import raygen
     from oracle import port
@@ -184,20 +184,21 @@ def test_full_frame_properties_and_subsample_parity(api):
     big = b > 1.0
     assert np.abs(np.sum(nrm * ep, axis=1))[big].max() / 60.0 < 0.15   # default-tolerance drift only (oracle: 0.093)
     # strided subsample against the oracle
-    sel = np.arange(0, n, 16)
-    o = port.trace(pos[sel], d[sel])
+    sel = np.arange(0, n)
+    o = port.trace(pos, d)
     band = ~away[sel]
-    # Pole-grazing rays: when the orbital plane contains the polar axis (|n_z| < 3e-3, 1 % of this frame) the ray can
+    # Pole-grazing rays: when the orbital plane contains the polar axis (|n_z| < 1e-2, 1.4 % of this frame) the ray can
     # pass through the coordinate singularity of the reference's spherical formulation, where cot(theta) amplifies
     # round-off without bound: the CPU restatement differs from scipy itself by 4e-6 on such rays, the CUDA path
-    # from the CPU restatement by up to 3e-5 (profiles/r1q_pole_outliers.json) - with identical step counts.  They
-    # are held to status equality, identical step counts and a loose 1e-3; every other ray to 1e-6.
-    pole = np.abs(nrm[sel, 2]) < 3e-3
+    # from the CPU restatement by up to 3e-5 on 7 rays of this frame, all with |n_z| < 6e-3
+    # (profiles/r1q_pole_outliers.json) - with identical step counts.  They are held to status equality, identical
+    # step counts and a loose 1e-3; every other ray to 1e-6.
+    pole = np.abs(nrm[sel, 2]) < 1e-2
     assert_parity(ep[sel], ed[sel], st[sel], o["exit_pos"], o["exit_dir"], o["status"], 60.0, exclude=band | pole)
     assert_parity(ep[sel], ed[sel], st[sel], o["exit_pos"], o["exit_dir"], o["status"], 60.0, exclude=band | ~pole,
                   pos_rtol=1e-3, dir_atol=1e-3)
     dev_pole = np.abs(ep[sel] - o["exit_pos"]).max(axis=1)[pole & ~band & (st[sel] == 0)] / 60.0
-    assert (dev_pole > 1e-6).mean() < 0.01      # even there, almost all rays agree tightly
+    assert (dev_pole > 1e-6).mean() < 1e-3      # even there, almost all rays agree tightly
     same_steps = (cnt[0][sel][~band] == o["n_attempt"][~band]).mean()
     assert same_steps > 0.9999
     print(f"full frame: attempts/ray {att / n:.2f}, captured {100 * (~esc).mean():.3f}%, identical step counts on "
