@@ -111,6 +111,11 @@ def cpu_baseline_sample(target=20480):
     return pos[sel], d[sel], stride
 
 
+def raygen_r_sphere():
+    from blackhole_geodesic_calculator_b200 import raygen
+    return float(raygen.CFG_R_SPHERE)
+
+
 def time_reference(pos, d, processes):
     """The reference's method (sympy RHS + scipy.solve_ivp RK45, one Python call per ray) on host cores."""
     import multiprocessing as mp
@@ -390,11 +395,37 @@ def run_b200(args):
             cores = os.cpu_count() or 1
             cpos, cdir, stride = cpu_baseline_sample(min(20480, max(256, 250 * cores * 12)))  # ~12 s of work
             m = cpos.shape[0]
-            rate, dt, _ = time_reference(cpos, cdir, cores)
+            rate, dt, cpu_out = time_reference(cpos, cdir, cores)
             line["cpu_baseline"] = {"value": rate, "unit": "rays/s", "cores": cores, "kind": "port",
                                     "sample": f"every {stride}th ray of frame 0 ({m} rays) in {dt:.1f} s; "
                                               "restated reference method (sympy RHS + scipy.solve_ivp RK45 per ray, "
                                               "multiprocessing Pool over all cores)"}
+            if args.mode == "parity" and not args.disk:
+                try:
+                    # the CPU arm just integrated every `stride`-th ray of the frame the GPU traced: compare them
+                    sel = torch.arange(0, n, stride, device=dev)
+                    g_pos, g_dir = exit_pos.index_select(0, sel).cpu().numpy(), exit_dir.index_select(0, sel).cpu().numpy()
+                    g_st = status.index_select(0, sel).cpu().numpy()
+                    g_acc = counters[1].index_select(0, sel).cpu().numpy()
+                    c_pos, c_dir, c_st, _, c_acc = cpu_out[:5]
+                    esc = (c_st == 0) & (g_st == 0)
+                    nrm = np.cross(cpos, cdir)
+                    pole = np.abs(nrm[:, 2]) / np.linalg.norm(nrm, axis=1) < 1e-2   # orbital plane contains the polar axis
+                    dpos = np.abs(g_pos - c_pos).max(axis=1) / raygen_r_sphere()
+                    ddir = np.abs(g_dir - c_dir).max(axis=1)
+                    line["parity_vs_cpu_sample"] = {
+                        "rays": int(m), "status_equal": bool((g_st == c_st).all()),
+                        "accepted_steps_equal_frac": float((g_acc == c_acc).mean()),
+                        "max_rel_dpos_escaped": float(dpos[esc & ~pole].max()),
+                        "max_ddir_escaped": float(ddir[esc & ~pole].max()),
+                        "pole_grazing": {"rays": int((esc & pole).sum()), "over_1e-6": int((dpos[esc & pole] > 1e-6).sum()),
+                                         "max_rel_dpos": float(dpos[esc & pole].max(initial=0.0))},
+                        "note": "GPU results of the timed frame against the scipy arm on the same rays; rays whose "
+                                "orbital plane contains the polar axis (|n_z| < 1e-2) cross the coordinate singularity "
+                                "of the reference's formulation and are listed apart (DESIGN.md section 2); "
+                                "informational - the parity gate is tests/ (pytest -m gpu)"}
+                except Exception as e:  # informational block: never lose the bench line over it
+                    line["parity_vs_cpu_sample"] = {"error": str(e)}
             try:
                 from oracle import port
                 t0 = time.perf_counter()
