@@ -168,3 +168,24 @@ def _nccl_worker(rank, world, port, q):
             frame.close()
     finally:
         dist.destroy_process_group()
+
+
+def test_peer_frame_single_process_routes_equal_plain_trace():
+    """PeerFrame without a process group (world 1): both delivery routes run through bhg_device_alloc, the `order`
+    array / bhg_copy_rows on one GPU and must reproduce the plain call bit for bit, ragged frame included."""
+    import torch
+    from blackhole_geodesic_calculator_b200 import api, distributed, raygen
+    pos, d = raygen.config_bundle(64, 64, 3)
+    tp, td = torch.from_numpy(pos).cuda(), torch.from_numpy(d).cuda()
+    for n, width in ((tp.shape[0], 64), (tp.shape[0], 0), (8192 + 77, 0)):
+        p, q = tp[:n].contiguous(), td[:n].contiguous()
+        ref = api.trace(p, q)
+        frame = distributed.PeerFrame(n)
+        try:
+            for route, chunks in (("stores", 1), ("copy", 1), ("copy", 3)):
+                frame.tensors()[2].fill_(-7)
+                got = distributed.trace_sharded_peer(p, q, frame, image_width=width, route=route, chunks=chunks)
+                torch.cuda.synchronize()
+                assert all(torch.equal(a, b) for a, b in zip(got, ref)), (n, width, route, chunks)
+        finally:
+            frame.close()
