@@ -427,6 +427,28 @@ def run_b200(args):
                 except Exception as e:  # informational block: never lose the bench line over it
                     line["parity_vs_cpu_sample"] = {"error": str(e)}
             try:
+                # the two other figures SURVEY.md section 8(d) asks for: one process, and the RRE call shape
+                # (no sphere, lambda in [0, 50], 10 000 t_eval samples per ray of which the engine reads the last:
+                # RelativisticRenderEngine.py:293-294,307-308)
+                from oracle import schwarzschild_ref as R
+                from blackhole_geodesic_calculator_b200 import raygen
+                k1 = min(512, m)
+                t0 = time.perf_counter()
+                R.trace(cpos[:k1], cdir[:k1], 1.0, raygen.CFG_R_SPHERE, 1e-3, 1e-6)
+                line["cpu_baseline"]["single_process_rays_per_s"] = k1 / (time.perf_counter() - t0)
+                rot = raygen.look_at_rotation((12.0, -8.0, 4.0))
+                rd = raygen.camera_rays(16, 16, 1, 1.0, 1.0, rot, 42, "philox")
+                rp = np.tile([12.0, -8.0, 4.0], (rd.shape[0], 1))
+                t0 = time.perf_counter()
+                R.trace_pool(rp, rd, cores, chunk=max(1, rd.shape[0] // (2 * cores)), M=0.5, r_sphere=np.inf,
+                             lambda_max=50.0, polyline=10000)
+                line["cpu_baseline"]["rre_call_shape_rays_per_s"] = rd.shape[0] / (time.perf_counter() - t0)
+                line["cpu_baseline"]["rre_call_shape_sample"] = ("256 rays from a camera at (12,-8,4) M, M=0.5, no "
+                                                                 "sphere, curve_end=50, nr_points_curve=10000, Pool "
+                                                                 "over all cores (includes starting the pool)")
+            except Exception as e:
+                line["cpu_baseline"]["extra_shapes_error"] = str(e)
+            try:
                 from oracle import port
                 t0 = time.perf_counter()
                 port.trace(cpos, cdir)
