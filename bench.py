@@ -101,12 +101,13 @@ _FRAME0 = None
 
 def cpu_baseline_sample(target=20480):
     """Bounded sample of the same workload for the CPU arm: a strided subsample of frame 0 with about
-    `target` rays (stride 256 -> 20 480 rays), so that it covers the whole image including the shadow."""
+    `target` rays (stride 257 -> 20 401 rays), so that it covers the whole image including the shadow."""
     global _FRAME0
     if _FRAME0 is None:
         _FRAME0 = frame_rays(0)
     pos, d = _FRAME0
-    stride = max(1, pos.shape[0] // max(int(target), 1))
+    stride = max(1, pos.shape[0] // max(int(target), 1)) | 1   # odd: coprime with the image width, so the sample
+    # walks diagonally through the image instead of picking 4 columns (one of them the pole-grazing centre line)
     sel = np.arange(0, pos.shape[0], stride)
     return pos[sel], d[sel], stride
 

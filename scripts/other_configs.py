@@ -40,4 +40,19 @@ for name, inplane in (("cfg5_3d", False), ("cfg5_inplane", True)):
     best = min(v for k, v in rec.items() if k.startswith("ms_T"))
     rec["best_rays_per_s"] = (1 << 20) / best * 1e3
     out[name] = rec
+# RRE call shape (RelativisticRenderEngine.py:293-294): camera inside the curved region, no sphere, fixed affine
+# length 50, M = 0.5; 1024 x 1024 rays, only the end state is consumed (RRE.py:307-308)
+rot = raygen.look_at_rotation((12.0, -8.0, 4.0))
+dr = raygen.camera_rays(1024, 1024, 1, 1.0, 1.0, rot, 42, "philox")
+pr = np.tile([12.0, -8.0, 4.0], (dr.shape[0], 1))
+tp, td = torch.from_numpy(pr).cuda(), torch.from_numpy(dr).cuda()
+kw = dict(M=0.5, r_sphere=float("inf"), lambda_max=50.0)
+ep, ed, st, cnt = api.trace(tp, td, return_counters=True, **kw)
+rec = {"rays": dr.shape[0], "attempts_per_ray": cnt[0].double().mean().item(),
+       "status_counts": torch.bincount(st.long(), minlength=6).tolist()}
+for width in (0, 1024):
+    ms = timeit(lambda: api.trace(tp, td, image_width=width, **kw))
+    rec[f"ms_w{width}"] = ms
+rec["rays_per_s"] = dr.shape[0] / min(rec["ms_w0"], rec["ms_w1024"]) * 1e3
+out["rre_call_shape"] = rec
 print(json.dumps(out, indent=1))
