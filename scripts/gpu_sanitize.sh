@@ -12,6 +12,20 @@ for kw in (dict(), dict(mode="plane"), dict(disk=(6.0, 20.0)), dict(refill_thres
 rot = raygen.look_at_rotation(raygen.CFG_CAMERA_POS)
 cam = api.make_camera(raygen.CFG_CAMERA_POS, rot, 48, 40, 1.0, 1.0, jitter="philox")
 print(np.bincount(api.trace_camera(cam, 48 * 40)[2], minlength=6), api.trace_camera_sky(cam, 48 * 40)[0].shape)
+# polyline output, float32 I/O, peer-frame routes (single process)
+res = api.trace(pos[:256], d[:256], lambda_max=200.0, polyline=17)
+print("poly", res[3].shape, int(res[4].min()), int(res[4].max()))
+f = api.trace_f32(pos.astype(np.float32), d.astype(np.float32))
+print("f32", np.bincount(f[2], minlength=6))
+import torch
+from blackhole_geodesic_calculator_b200 import distributed
+tp, td = torch.from_numpy(pos).cuda(), torch.from_numpy(d).cuda()
+frame = distributed.PeerFrame(tp.shape[0])
+for route, chunks, w in (("stores", 1, 48), ("copy", 3, 48), ("copy", 2, 0)):
+    got = distributed.trace_sharded_peer(tp, td, frame, route=route, chunks=chunks, image_width=w)
+    torch.cuda.synchronize()
+    print(route, chunks, w, torch.bincount(got[2].long(), minlength=6).tolist())
+frame.close()
 PY
 for tool in memcheck racecheck initcheck; do
   timeout 600 compute-sanitizer --tool $tool --error-exitcode 7 python /tmp/san.py > gpurun_out/sanitizer_$tool.log 2>&1; echo "$tool rc=$?" | tee -a gpurun_out/sanitizer_$tool.log
