@@ -337,3 +337,45 @@ def trace_sharded_peer(entry_pos, entry_dir, frame: PeerFrame, *, image_width=0,
         cur.wait_stream(side)
     frame.fence()
     return frame.tensors()
+
+
+class PeerFrameGraph:
+    """One `trace_sharded_peer` call captured in a CUDA graph and replayed per frame.
+
+    At 8 GPUs a 5.2 M-ray frame is 0.9 ms of device work issued through ~25 host calls (two fences, the compaction,
+    two trace pieces, their strided deliveries); driven from Python the GPU waits for the host at the start of every
+    frame.  The captured graph replays the whole sequence, NCCL fences included, with one launch.
+    `entry_pos` / `entry_dir` are static buffers: refill them in place (e.g. `api.generate_rays(..., out=...)` or
+    `copy_`) before each `replay()`.  Collective: build and replay on every rank."""
+
+    def __init__(self, entry_pos, entry_dir, frame: PeerFrame, **kw):
+        import torch
+
+        self.frame, self.kw = frame, kw
+        dev = entry_pos.device
+        cur = torch.cuda.current_stream(dev)
+        warm = torch.cuda.Stream(dev)
+        warm.wait_stream(cur)
+        with torch.cuda.stream(warm):   # library / NCCL / plan initialisation must not happen under capture
+            for _ in range(2):
+                trace_sharded_peer(entry_pos, entry_dir, frame, **kw)
+        cur.wait_stream(warm)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = trace_sharded_peer(entry_pos, entry_dir, frame, **kw)
+
+    def replay(self):
+        self.graph.replay()
+        return self.out
+
+    def close(self):
+        """Release the captured graph.  Call it on every rank BEFORE `frame.close()` / destroying the process group:
+        a live graph keeps the captured NCCL work alive and `destroy_process_group` then waits forever."""
+        import torch
+
+        torch.cuda.synchronize(self.frame.device)
+        self.out = None
+        if self.graph is not None:
+            self.graph.reset()
+            self.graph = None

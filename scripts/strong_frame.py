@@ -31,7 +31,8 @@ def main():
     pos, d, _ = api.generate_rays(cam, 4 * 1280 * 1024, raygen.CFG_R_SPHERE, device=local)   # device generator, same on all ranks
     kw = dict(M=raygen.CFG_M, r_sphere=raygen.CFG_R_SPHERE, rtol=1e-3, atol=1e-6)
     res = {}
-    for chunks in (1, 2, 4, 8):
+    quick = os.environ.get("BHG_STRONG_QUICK", "0") == "1"   # fewer variants: an 8-GPU box is charged 8x
+    for chunks in ((2,) if quick else (1, 2, 4, 8)):
         times = []
         for it in range(8):
             if world > 1:
@@ -51,8 +52,11 @@ def main():
     # peer-memory route: exit states stored straight into rank 0's HBM by every GPU's trace kernel
     frame = D.PeerFrame(pos.shape[0], owner=0)
     peer = {}
-    for route, width, chunks in (("stores", 0, 1), ("stores", 1280, 1), ("copy", 0, 1), ("copy", 1280, 1),
-                                 ("copy", 1280, 2), ("copy", 1280, 4), ("copy", 1280, 8)):
+    variants = (("stores", 0, 1), ("stores", 1280, 1), ("copy", 0, 1), ("copy", 1280, 1), ("copy", 1280, 2),
+                ("copy", 1280, 4), ("copy", 1280, 8))
+    if quick:
+        variants = (("stores", 0, 1), ("copy", 1280, 2))
+    for route, width, chunks in variants:
         times = []
         for it in range(10):
             if world > 1:
@@ -72,11 +76,41 @@ def main():
     same = None
     if rank == 0:
         same = all(torch.equal(a, b) for a, b in zip(pout, out))
+    # the same call captured in a CUDA graph (one launch per frame instead of ~25 host calls)
+    graphs = {}
+    if os.environ.get("BHG_STRONG_GRAPHS", "0") == "1":
+        for route, width, chunks in (("stores", 0, 1), ("copy", 1280, 2)):
+            try:
+                if rank == 0:
+                    pout[2].fill_(-9)
+                g = D.PeerFrameGraph(pos, d, frame, image_width=width, route=route, chunks=chunks, **kw)
+                times = []
+                for it in range(10):
+                    if world > 1:
+                        dist.barrier()
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    gout = g.replay()
+                    e1.record()
+                    torch.cuda.synchronize()
+                    t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+                    if world > 1:
+                        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    if it >= 3:
+                        times.append(float(t))
+                graphs[f"{route}/w{width}/c{chunks}"] = float(np.median(times))
+                if rank == 0:
+                    graphs[f"{route}/w{width}/c{chunks}/equal"] = all(torch.equal(a, b) for a, b in zip(gout, out))
+                g.close()
+                del g, gout
+            except Exception as e:  # report instead of losing the other numbers
+                graphs[f"{route}/error"] = repr(e)[:300]
     frame.close()
     if rank == 0:
         n = pos.shape[0]
         st = out[2]
-        print(json.dumps({"n_gpus": world, "rays": n, "gather_frame_ms_by_chunks": res, "peer_frame_ms": peer,
+        print(json.dumps({"n_gpus": world, "rays": n, "gather_frame_ms_by_chunks": res, "peer_frame_ms": peer, "peer_frame_graph_ms": graphs,
                           "peer_equals_gather": same, "best_rays_per_s": n / (min(peer.values()) * 1e-3),
                           "status_counts": torch.bincount(st.to(torch.int64), minlength=6).tolist()}))
     if world > 1:
