@@ -189,3 +189,29 @@ def test_peer_frame_single_process_routes_equal_plain_trace():
                 assert all(torch.equal(a, b) for a, b in zip(got, ref)), (n, width, route, chunks)
         finally:
             frame.close()
+
+
+def test_peer_frame_graph_replay_single_process():
+    """The sharded-frame call is capturable in a CUDA graph (memset of the queue head, trace kernels on two streams,
+    strided copy-engine deliveries) and the replay reproduces the plain call after the inputs changed in place."""
+    import torch
+    from blackhole_geodesic_calculator_b200 import api, distributed, raygen
+    pos, d = raygen.config_bundle(64, 64, 2)
+    tp, td = torch.from_numpy(pos).cuda(), torch.from_numpy(d).cuda()
+    frame = distributed.PeerFrame(tp.shape[0])
+    try:
+        for route, chunks in (("stores", 1), ("copy", 2)):
+            g = distributed.PeerFrameGraph(tp, td, frame, image_width=64, route=route, chunks=chunks)
+            try:
+                # new frame in the same static buffers: mirror the rays through the equatorial plane
+                flip = torch.tensor([1.0, 1.0, -1.0], dtype=torch.float64, device="cuda")
+                tp.mul_(flip)
+                td.mul_(flip)
+                got = g.replay()
+                torch.cuda.synchronize()
+                ref = api.trace(tp, td)
+                assert all(torch.equal(a, b) for a, b in zip(got, ref)), route
+            finally:
+                g.close()
+    finally:
+        frame.close()
