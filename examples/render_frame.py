@@ -39,8 +39,8 @@ def main():
     n = spp * w * h
     t0 = time.perf_counter()
     pos, d, hit = api.generate_rays(cam, n, R)                       # device tensors, loop order s -> y -> x
-    exit_pos, exit_dir, status, disk_xy = api.trace(pos.cpu().numpy(), d.cpu().numpy(), M=M, r_sphere=R, rtol=rtol,
-                                                    atol=rtol * 1e-3, image_width=w, disk=(6.0, 22.0))
+    res = api.trace(pos, d, M=M, r_sphere=R, rtol=rtol, atol=rtol * 1e-3, image_width=w, disk=(6.0, 22.0))
+    exit_pos, exit_dir, status, disk_xy = (t.cpu().numpy() for t in res)   # device tensors in, device tensors out
     dt = time.perf_counter() - t0
     # sky: equirectangular checkerboard tinted by direction, as background_hit would sample a texture
     phi = np.arctan2(exit_dir[:, 1], exit_dir[:, 0])
@@ -57,7 +57,7 @@ def main():
     rgb[on_disk] = np.stack([np.minimum(1.0, 1.6 * glow), np.minimum(1.0, 0.9 * glow), 0.35 * glow], axis=1)
     img = rgb.reshape(spp, h, w, 3).mean(axis=0)
     write_png(out, (np.clip(img, 0, 1) ** (1 / 2.2) * 255).astype(np.uint8))
-    print(f"{out}: {w}x{h} x {spp} spp = {n} rays generated + traced (host arrays) in {dt * 1e3:.1f} ms; "
+    print(f"{out}: {w}x{h} x {spp} spp = {n} rays generated + traced + copied to the host in {dt * 1e3:.1f} ms; "
           f"captured {100 * (status == 1).mean():.2f} %, on disk {100 * on_disk.mean():.2f} %")
 
 
