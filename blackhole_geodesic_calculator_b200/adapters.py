@@ -166,6 +166,32 @@ class SchwarzschildGeodesic:
         return pts[:, 0], pts[:, 1], pts[:, 2], ep[0] / scale, ed[0], mes
 
 
+class ApproxSchwarzschildGeodesic:
+    """Call shape of curvedpy's tabulated approximate tracer (LimitedRelativisticRenderEngine.py:39-40,97-101,269):
+    `ApproxSchwarzschildGeodesic(ratio_obj_to_blackhole=, exit_tolerance=).generatedRayTracer(loc, direction)` ->
+    (end_loc, end_dir, mes).  The reference interpolates a pre-computed table because the exact solve is slow; here
+    the exact solve is the fast path, so the same call is answered exactly (no table, no interpolation error) and
+    the engine's `approx` branch keeps working unchanged.  `generatedRayTracer_batch` is the batched form."""
+
+    def __init__(self, ratio_obj_to_blackhole=30.0, exit_tolerance=0.2, device=0):
+        self.ratio_obj_to_blackhole = float(ratio_obj_to_blackhole)   # attributes read back by the engine (LIM.py:97-98)
+        self.exit_tolerance = float(exit_tolerance)
+        self._exact = SchwarzschildGeodesic(device=device)
+
+    def generatedRayTracer_batch(self, locs, directions):
+        end_loc, end_dir, hit_bh, outside, status = self._exact.ray_trace_batch(
+            directions, locs, exit_tolerance=self.exit_tolerance, ratio_obj_to_blackhole=self.ratio_obj_to_blackhole)
+        return end_loc, end_dir, hit_bh, outside, status
+
+    def generatedRayTracer(self, loc, direction):
+        end_loc, end_dir, hit_bh, outside, status = self.generatedRayTracer_batch(
+            np.asarray(loc, float).reshape(1, 3), np.asarray(direction, float).reshape(1, 3))
+        mes = {"hit_blackhole": bool(hit_bh[0]), "status": int(status[0])}
+        if outside[0]:
+            mes["error"] = "Outside"
+        return end_loc[0], end_dir[0], mes
+
+
 class RelativisticCamera:
     """CAM call shape: a whole frame traced ahead of shading; the consumer reads `ray_blackhole_hit[iy,ix]`
     and `ray_end[iy,ix,3:6]` (RelativisticRenderEngineCamEdition.py:206-215,225-228).  `a` (spin) must be 0:

@@ -81,6 +81,14 @@ def test_lim_call_shape_scaling_and_messages():
     assert n_hit > 0
     x, y, z, el, ed, mes = sw.ray_trace(d[5], locs[5], ratio_obj_to_blackhole=ratio, curve_end=5.0)
     assert mes.get("error") == "Outside" and mes["hit_blackhole"] is False
+    # the engine's `approx` branch (LIM.py:97-101,269): same attributes, same call, answered exactly
+    asw = adapters.ApproxSchwarzschildGeodesic(ratio_obj_to_blackhole=ratio, exit_tolerance=0.2)
+    assert round(asw.exit_tolerance, 4) == 0.2 and round(asw.ratio_obj_to_blackhole, 4) == ratio
+    a_loc, a_dir, a_mes = asw.generatedRayTracer(locs[5], d[5])
+    assert np.array_equal(a_loc, end_loc[5]) and np.array_equal(a_dir, end_dir[5])
+    assert a_mes["hit_blackhole"] == bool(hit_bh[5]) and "error" not in a_mes
+    cap = int(np.nonzero(hit_bh)[0][0])
+    assert asw.generatedRayTracer(locs[cap], d[cap])[2]["hit_blackhole"] is True
 
 
 def test_cam_call_shape():
