@@ -166,6 +166,38 @@ class SchwarzschildGeodesic:
         return pts[:, 0], pts[:, 1], pts[:, 2], ep[0] / scale, ed[0], mes
 
 
+class Conversions:
+    """Host-side coordinate conversions under curvedpy's name (used by the engines only for a debug print,
+    RelativisticRenderEngine.py:289-291, RelativisticRenderEngineCamEdition.py:349): Cartesian position + tangent
+    <-> spherical (r, theta, phi) position + coordinate-basis components, the same map the tracer applies on the
+    device when a ray enters and leaves the integration (csrc/trace_kernel.cuh init_state / exit_state)."""
+
+    @staticmethod
+    def convert_xyz_to_sph(x_xyz, k_xyz):
+        x, y, z = (float(v) for v in x_xyz)
+        kx, ky, kz = (float(v) for v in k_xyz)
+        r = math.sqrt(x * x + y * y + z * z)
+        rho2 = x * x + y * y
+        rho = math.sqrt(rho2)
+        th, ph = math.acos(z / r), math.atan2(y, x)
+        k_r = (x * kx + y * ky + z * kz) / r
+        with np.errstate(all="ignore"):   # on the polar axis the spherical tangent is singular: inf / nan, no exception
+            k_th = float(np.float64(z * (x * kx + y * ky) - rho2 * kz) / np.float64(r * r * rho))
+            k_ph = float(np.float64(x * ky - y * kx) / np.float64(rho2))
+        return np.array([r, th, ph]), np.array([k_r, k_th, k_ph])
+
+    @staticmethod
+    def convert_sph_to_xyz(x_sph, k_sph):
+        r, th, ph = (float(v) for v in x_sph)
+        k_r, k_th, k_ph = (float(v) for v in k_sph)
+        st, ct, sp, cp = math.sin(th), math.cos(th), math.sin(ph), math.cos(ph)
+        x = np.array([r * st * cp, r * st * sp, r * ct])
+        k = np.array([k_r * st * cp + r * ct * cp * k_th - r * st * sp * k_ph,
+                      k_r * st * sp + r * ct * sp * k_th + r * st * cp * k_ph,
+                      k_r * ct - r * st * k_th])
+        return x, k
+
+
 class ApproxSchwarzschildGeodesic:
     """Call shape of curvedpy's tabulated approximate tracer (LimitedRelativisticRenderEngine.py:39-40,97-101,269):
     `ApproxSchwarzschildGeodesic(ratio_obj_to_blackhole=, exit_tolerance=).generatedRayTracer(loc, direction)` ->

@@ -71,3 +71,20 @@ def test_near_critical_bundle_has_requested_b():
     got = raygen.conserved_impact_parameter(pos, d, 1.0)
     assert np.abs(got - b).max() < 1e-12 and b.min() >= 5.0 and b.max() <= 5.4
     assert np.allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-14)
+
+
+def test_conversions_round_trip_and_match_the_oracle_entry_map():
+    """adapters.Conversions (curvedpy's name, RRE.py:289-291): xyz -> sph -> xyz is the identity, and the spherical
+    components are the ones the oracle starts its integration from."""
+    from blackhole_geodesic_calculator_b200 import adapters
+    from oracle import schwarzschild_ref as R
+    rng = np.random.default_rng(3)
+    conv = adapters.Conversions()
+    for _ in range(50):
+        x, k = rng.normal(size=3) * 20.0, rng.normal(size=3)
+        xs, ks = conv.convert_xyz_to_sph(x, k)
+        x2, k2 = conv.convert_sph_to_xyz(xs, ks)
+        assert np.allclose(x2, x, rtol=1e-13, atol=1e-13) and np.allclose(k2, k, rtol=1e-12, atol=1e-13)
+        if hasattr(R, "xyz_to_sph"):
+            xo, ko = R.xyz_to_sph(x, k)
+            assert np.allclose(xs, xo, rtol=1e-13) and np.allclose(ks, ko, rtol=1e-12, atol=1e-14)
