@@ -27,6 +27,9 @@ sys.path.insert(0, ROOT)
 
 W, H, SPP = 1024, 1024, 5
 FLOP_FIXED, FLOP_PER_ATTEMPT = 230.0, 760.0  # FLOP(ray) = 230 + 760 * n_attempt
+# the optional plane mode integrates 6 variables instead of 8: RHS 22 flops (csrc/geodesic_core.cuh Rhs<3>) instead of
+# 40, Runge-Kutta algebra 6/8 of 520 -> 6 * 22 + 390 = 522 per attempt; fixed part without the theta conversions
+FLOP_FIXED_PLANE, FLOP_PER_ATTEMPT_PLANE = 200.0, 522.0
 NOMINAL_FP64_TFLOPS = 37.2                   # 148 SM x 64 FMA/clk x 2 x 1.965 GHz
 
 
@@ -221,7 +224,10 @@ def run_b200(args):
     step(with_counters=True)
     torch.cuda.synchronize(dev)
     att, acc, integ = api.sum_counters(counters.data_ptr(), status.data_ptr(), n, local, stream.cuda_stream)
-    flop_per_launch = FLOP_FIXED * integ + FLOP_PER_ATTEMPT * att
+    if args.mode == "plane":
+        flop_per_launch = FLOP_FIXED_PLANE * integ + FLOP_PER_ATTEMPT_PLANE * att
+    else:
+        flop_per_launch = FLOP_FIXED * integ + FLOP_PER_ATTEMPT * att
 
     # clocks are sampled from before the warm-up to the end of the timed region (same load throughout); the warm-up
     # runs at least W steps and at least 0.4 s so that nvidia-smi is up and several samples fall under load
