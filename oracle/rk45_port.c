@@ -96,8 +96,37 @@ static void rhs6(const double* y, double rs, double* f) {
     f[5] = k_ph;
 }
 
+/* Conditioning probe (tests only): with a non-zero jitter seed every RHS evaluation is made "backward-stably
+ * wrong" by one ulp: each state entry the formulas read is multiplied by 1 + s * 2^-52 before the evaluation and each
+ * momentum derivative by another such factor after it, s in {-1, 0, +1} from a per-ray generator.  That is the
+ * rounding freedom any other implementation of the same formulas has (operation order, FMA contraction, a 1-ulp
+ * reciprocal or sine; cancellation between the large terms of dk_r is included because the INPUTS move).  How far a
+ * ray's exit state moves under this jitter is the accuracy to which two implementations of the reference's
+ * method can agree on that ray; tests/ use it as the per-ray tolerance floor. */
+static uint64_t g_jitter_seed = 0;
+static __thread uint64_t g_jitter_state = 0;
+
+void bhg_oracle_set_jitter(uint64_t seed) { g_jitter_seed = seed; }
+
+static inline uint64_t jitter_next(void) { /* splitmix64 */
+    uint64_t z = (g_jitter_state += 0x9E3779B97F4A7C15ULL);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
 static void rhs(const sys_t* S, const double* y, double* f) {
-    if (S->n == 8) rhs8(y, S->rs, f); else rhs6(y, S->rs, f);
+    if (!g_jitter_seed) {
+        if (S->n == 8) rhs8(y, S->rs, f); else rhs6(y, S->rs, f);
+        return;
+    }
+    double yj[NMAX];
+    uint64_t r = jitter_next();
+    for (int i = 0; i < S->n; i++, r >>= 4) yj[i] = y[i] * (1.0 + (double)((int)(r % 3) - 1) * DBL_EPSILON);
+    if (S->n == 8) rhs8(yj, S->rs, f); else rhs6(yj, S->rs, f);
+    r = jitter_next();
+    for (int i = 0; i < S->n; i += 2, r >>= 4) f[i] *= 1.0 + (double)((int)(r % 3) - 1) * DBL_EPSILON;
+    for (int i = 1; i < S->n; i += 2) f[i] = y[i - 1];  /* dx/dlambda = k exactly, as in every implementation */
 }
 
 static double rms(const double* x, int n) { /* common.py:63-65 */
@@ -456,6 +485,7 @@ static void* worker(void* arg) {
         int64_t e = b + 64 < J->n ? b + 64 : J->n;
         for (int64_t i = b; i < e; i++) {
             ray_out_t o;
+            g_jitter_state = g_jitter_seed ^ ((uint64_t)i * 0xD1B54A32D192ED03ULL);
             if (J->mode == 0)
                 trace_parity(J->pos + 3 * i, J->dir + 3 * i, J->M, J->r_sphere, J->rtol, J->atol, J->max_step, J->eps,
                              J->lambda_max, &J->disk, J->exit_pos + 3 * i, J->exit_dir + 3 * i, &o);

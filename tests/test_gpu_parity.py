@@ -8,7 +8,8 @@ import ctypes
 import numpy as np
 import pytest
 
-from conftest import B_CRIT_BAND, assert_parity, golden_kwargs, load_golden
+from conftest import (B_CRIT_BAND, COND_K, COND_SEEDS, COND_WELL, assert_conditioned_parity, assert_parity, golden_kwargs,
+                      load_golden, ray_deviation)
 
 pytestmark = pytest.mark.gpu
 
@@ -183,26 +184,16 @@ def test_full_frame_properties_and_subsample_parity(api):
     nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
     big = b > 1.0
     assert np.abs(np.sum(nrm * ep, axis=1))[big].max() / 60.0 < 0.15   # default-tolerance drift only (oracle: 0.093)
-    # strided subsample against the oracle
-    sel = np.arange(0, n)
+    # every ray against the oracle's C restatement under the per-ray conditioning rule (conftest.py): rays whose
+    # oracle result does not move under 1-ulp RHS jitter (all but a handful: the pole-grazing ones) must have
+    # identical step counts and agree to 1e-6 without exception; statuses equal on every ray, also inside the
+    # +-1e-2 M band around b_crit.
     o = port.trace(pos, d)
-    band = ~away[sel]
-    # Pole-grazing rays: when the orbital plane contains the polar axis (|n_z| < 1e-2, 1.4 % of this frame) the ray can
-    # pass through the coordinate singularity of the reference's spherical formulation, where cot(theta) amplifies
-    # round-off without bound: the CPU restatement differs from scipy itself by 4e-6 on such rays, the CUDA path
-    # from the CPU restatement by up to 3e-5 on 7 rays of this frame, all with |n_z| < 6e-3
-    # (profiles/r1q_pole_outliers.json) - with identical step counts.  They are held to status equality, identical
-    # step counts and a loose 1e-3; every other ray to 1e-6.
-    pole = np.abs(nrm[sel, 2]) < 1e-2
-    assert_parity(ep[sel], ed[sel], st[sel], o["exit_pos"], o["exit_dir"], o["status"], 60.0, exclude=band | pole)
-    assert_parity(ep[sel], ed[sel], st[sel], o["exit_pos"], o["exit_dir"], o["status"], 60.0, exclude=band | ~pole,
-                  pos_rtol=1e-3, dir_atol=1e-3)
-    dev_pole = np.abs(ep[sel] - o["exit_pos"]).max(axis=1)[pole & ~band & (st[sel] == 0)] / 60.0
-    assert (dev_pole > 1e-6).mean() < 1e-3      # even there, almost all rays agree tightly
-    same_steps = (cnt[0][sel][~band] == o["n_attempt"][~band]).mean()
-    assert same_steps > 0.9999
-    print(f"full frame: attempts/ray {att / n:.2f}, captured {100 * (~esc).mean():.3f}%, identical step counts on "
-          f"{100 * same_steps:.4f}% of {int((~band).sum())} compared rays")
+    cond, _ = port.conditioning(pos, d, base=o, seeds=COND_SEEDS)
+    res = assert_conditioned_parity(ep, ed, st, cnt[0], cnt[1], o, cond, 60.0, label="config 2 full frame")
+    assert res["ill_conditioned"] < 1e-4 * n and res["steps_differ"] <= 5
+    print(f"full frame: attempts/ray {att / n:.2f}, captured {100 * (~esc).mean():.3f}%, in the +-1e-2 M band "
+          f"{int((~away).sum())} rays (statuses equal there too)")
 
 
 def test_time_reversal_on_gpu(api):
@@ -466,42 +457,59 @@ def test_polyline_samples(api, name):
 
 def test_full_size_configs_3_and_5_against_c_port(api):
     """BASELINE configs 3 (1920x1080 frame, 2.03 M rays) and 5 (2^20 near-critical rays, in the equatorial plane and
-    in random planes) at full size against the C restatement, every ray (measured: profiles/r1r_full_parity_probe.json).
+    in random planes) at full size against the C restatement, every ray, under the per-ray conditioning rule
+    (conftest.py; adjudicated three-way against real scipy in profiles/r2a_adjudication.json):
 
     * statuses equal on every ray of all three sets, inside and outside the +-1e-2 M band around b_crit;
-    * config 3 and the in-plane config 5: identical step counts on every ray; exit states within 1e-6 (config 3, apart
-      from planes within 3 degrees of the polar axis) and 1e-7 (in-plane, where the reference's coordinates are regular:
-      measured 9e-9 on rays that orbit the photon sphere several times);
-    * config 5 in random planes: near-critical rays cross the polar region of the reference's coordinates on every
-      half orbit; round-off amplified there flips an accept/reject decision on ~1e-4 of the rays, after which the two
-      runs are different - equally valid - discretisations that agree only to the global error of rtol = 1e-3
-      (up to 2e-2 on such rays).  Held to: statuses equal, identical step counts on > 99.9 %, > 1e-6 on < 0.2 %."""
+    * every ray whose oracle result is insensitive to 1-ulp RHS jitter (conditioning < 1e-7: all of the in-plane set,
+      all but a few pole-grazing rays of config 3, 99.6 % of config 5 in random planes): identical step counts and
+      exit states within 1e-6, no exceptions (in-plane set: 1e-7);
+    * the ill-conditioned rest (near-critical rays that cross the polar region of the reference's coordinates on
+      every half orbit): within max(1e-6, 10 x conditioning), at most 1 ray in 10^5 beyond that.  scipy and its own C
+      restatement differ from each other on the same rays by the same amounts (79 / 624 rays with different step
+      counts / beyond 1e-6 there, 91 / 678 for the CUDA path)."""
     from blackhole_geodesic_calculator_b200 import raygen
     from oracle import port
 
-    def compare(p, d):
+    def compare(p, d, label):
         p, d = np.ascontiguousarray(p), np.ascontiguousarray(d)
         ep, ed, st, cnt = api.trace(p, d, return_counters=True)
         o = port.trace(p, d)
-        nrm = np.cross(p, d)
-        nz = np.abs(nrm[:, 2]) / np.linalg.norm(nrm, axis=1)
-        esc = (st == 0) & (o["status"] == 0)
-        dev = np.maximum(np.abs(ep - o["exit_pos"]).max(axis=1) / 60.0, np.abs(ed - o["exit_dir"]).max(axis=1))
-        steps = (cnt[0] == o["n_attempt"]) & (cnt[1] == o["n_accept"])
-        return st, o["status"], steps, esc, dev, nz
+        cond, _ = port.conditioning(p, d, base=o, seeds=COND_SEEDS)
+        res = assert_conditioned_parity(ep, ed, st, cnt[0], cnt[1], o, cond, 60.0, label=label)
+        return res, ray_deviation(ep, ed, o["exit_pos"], o["exit_dir"], 60.0), st
 
-    st, ost, steps, esc, dev, nz = compare(*raygen.random_impact_bundle(None))
-    assert np.array_equal(st, ost) and steps.all()
-    assert dev[esc & (nz > 0.05)].max() < 1e-6 and (dev[esc] > 1e-6).sum() < 10 and dev[esc].max() < 1e-3
+    res, dev, st = compare(*raygen.random_impact_bundle(None), "config 3")
+    assert res["steps_differ"] == 0 and res["ill_conditioned"] < 200 and dev[st == 0].max() < 1e-3
 
     p5, d5, _ = raygen.near_critical_bundle(1 << 20, in_plane=True)
-    st, ost, steps, esc, dev, nz = compare(p5, d5)
-    assert np.array_equal(st, ost) and steps.all()
-    assert dev[esc].max() < 1e-7
+    res, dev, st = compare(p5, d5, "config 5 in-plane")
+    assert res["steps_differ"] == 0 and res["ill_conditioned"] == 0 and dev[st == 0].max() < 1e-7
 
     p5, d5, _ = raygen.near_critical_bundle(1 << 20, in_plane=False)
-    st, ost, steps, esc, dev, nz = compare(p5, d5)
-    assert np.array_equal(st, ost)
-    assert steps.mean() > 0.999 and (dev[esc] > 1e-6).mean() < 2e-3
-    print(f"config 5 (random planes): identical steps on {100 * steps.mean():.4f} %, "
-          f"{int((dev[esc] > 1e-6).sum())} of {int(esc.sum())} escaped rays beyond 1e-6, max {dev[esc].max():.2e}")
+    res, dev, st = compare(p5, d5, "config 5 random planes")
+    assert res["steps_differ"] < 200 and res["ill_conditioned"] < 0.01 * len(st)
+
+
+def test_adjudicated_outliers_against_scipy_golden(api):
+    """The rays on which GPU, scipy and the C restatement disagreed pairwise in the round-2 adjudication
+    (tests/golden/parity_outliers.npz: config 5 random planes - every outlier of the 2^20 rays; configs 3 and 2 - the
+    GPU<->port outliers; plus control rays), CUDA path against the REAL scipy results, same per-ray rule."""
+    g = load_golden("parity_outliers.npz")
+    for name in ("cfg5", "cfg3", "cfg2"):
+        p, d = g[name + "_entry_pos"], g[name + "_entry_dir"]
+        ep, ed, st, cnt = api.trace(p, d, return_counters=True)
+        ref = dict(exit_pos=g[name + "_scipy_pos"], exit_dir=g[name + "_scipy_dir"], status=g[name + "_scipy_status"],
+                   n_attempt=g[name + "_scipy_attempt"], n_accept=g[name + "_scipy_accept"])
+        # the set is a selection of the worst rays of 1e6: the 1-in-1e5 allowance is taken over the full set size
+        dev = ray_deviation(ep, ed, ref["exit_pos"], ref["exit_dir"], 60.0)
+        cond = g[name + "_conditioning"]
+        assert np.array_equal(st, ref["status"]), name
+        cmp_ = np.isin(ref["status"], (0, 3))
+        well = cond < COND_WELL
+        same = (cnt[0] == ref["n_attempt"]) & (cnt[1] == ref["n_accept"])
+        assert same[well].all() and (dev[cmp_ & well] <= 1e-6).all(), name
+        viol = cmp_ & ~well & (dev > np.maximum(1e-6, COND_K * cond))
+        print(f"{name}: {len(st)} rays, ill-conditioned {int((cmp_ & ~well).sum())}, steps differ {int((~same).sum())}, "
+              f"beyond 1e-6 {int((cmp_ & (dev > 1e-6)).sum())}, beyond the conditioned bound {int(viol.sum())}")
+        assert viol.sum() <= 10, (name, np.nonzero(viol)[0], dev[viol], cond[viol])
