@@ -26,7 +26,7 @@ class BhgParams(ctypes.Structure):
         ("mode", ctypes.c_int32),
         ("refill_threshold", ctypes.c_int32),
         ("image_width", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("coords", ctypes.c_int32),
     ]
 
 

@@ -86,12 +86,22 @@ def spacetime_ray_cast_batch(integrator: GeodesicIntegratorSchwarzschild, origin
 class SchwarzschildGeodesic:
     """LIM call shape: entry point on the sphere of influence -> exit point/direction or capture
     (LimitedRelativisticRenderEngine.py:273-278).  The solver works in units of r_s (M = 1/2): the sphere
-    object of radius |loc_hit| is `ratio_obj_to_blackhole` horizon radii large (LIM.py:488, README.md:60)."""
+    object of radius |loc_hit| is `ratio_obj_to_blackhole` horizon radii large (LIM.py:488, README.md:60).
 
-    def __init__(self, metric="schwarzschild", device=0, rtol=1e-3, atol=1e-6, eps_horizon=0.01):
+    `coordinates`: chart in which `loc_hit` / `direction` are read and `end_loc` / `end_dir` / the polyline returned.
+    Default "isotropic": this curvedpy generation "uses the Schwarzschild metric in cartesian coordinates"
+    (README.md:174) and README Fig. 5 / Fig. 6, drawn with it, are reproduced to the pixel in the isotropic chart
+    and in no other (tests/test_readme_figures.py).  "schwarzschild" reads the same numbers as
+    x = r sin(th) cos(ph) of the Schwarzschild radius (the newer generation's chart, RelativisticRenderEngine.py:289)."""
+
+    def __init__(self, metric="schwarzschild", device=0, rtol=1e-3, atol=1e-6, eps_horizon=0.01,
+                 coordinates="isotropic"):
         if metric != "schwarzschild":
             raise NotImplementedError(f"metric {metric!r}: only 'schwarzschild' is on the reference's render path")
+        if coordinates not in api.COORDS:
+            raise ValueError(f"coordinates must be one of {sorted(api.COORDS)}")
         self.metric = metric
+        self.coordinates = coordinates
         self.device = device
         self.rtol, self.atol, self.eps_horizon = rtol, atol, eps_horizon
 
@@ -117,7 +127,8 @@ class SchwarzschildGeodesic:
         lam = self.approximateCurveEnd(ratio) if curve_end is None else float(curve_end)
         ms = math.inf if (max_step is None or max_step == -1) else float(max_step)
         res = api.trace(p * scale[:, None], d, 0.5, ratio, self.rtol, self.atol, max_step=ms,
-                        eps_horizon=self.eps_horizon, lambda_max=lam, mode=mode, device=self.device, disk=disk)
+                        eps_horizon=self.eps_horizon, lambda_max=lam, mode=mode, device=self.device, disk=disk,
+                        coords=self.coordinates)
         exit_pos, exit_dir, status = res[:3]
         hit_bh = status == api.CAPTURED
         # 'Outside': the ray did not end on the sphere within exit_tolerance (LIM.py:311-314)
@@ -155,7 +166,7 @@ class SchwarzschildGeodesic:
         ms = math.inf if (max_step is None or max_step == -1) else float(max_step)
         ep, ed, st, poly, cnt = api.trace(p * scale, d, 0.5, ratio, self.rtol, self.atol, max_step=ms,
                                           eps_horizon=self.eps_horizon, lambda_max=lam, device=self.device,
-                                          polyline=max(2, int(nr_points_curve)))
+                                          polyline=max(2, int(nr_points_curve)), coords=self.coordinates)
         status = int(st[0])
         hit_bh = status == api.CAPTURED
         off = abs(np.linalg.norm(ep[0]) - ratio) > exit_tolerance
@@ -205,10 +216,10 @@ class ApproxSchwarzschildGeodesic:
     the exact solve is the fast path, so the same call is answered exactly (no table, no interpolation error) and
     the engine's `approx` branch keeps working unchanged.  `generatedRayTracer_batch` is the batched form."""
 
-    def __init__(self, ratio_obj_to_blackhole=30.0, exit_tolerance=0.2, device=0):
+    def __init__(self, ratio_obj_to_blackhole=30.0, exit_tolerance=0.2, device=0, coordinates="isotropic"):
         self.ratio_obj_to_blackhole = float(ratio_obj_to_blackhole)   # attributes read back by the engine (LIM.py:97-98)
         self.exit_tolerance = float(exit_tolerance)
-        self._exact = SchwarzschildGeodesic(device=device)
+        self._exact = SchwarzschildGeodesic(device=device, coordinates=coordinates)
 
     def generatedRayTracer_batch(self, locs, directions):
         end_loc, end_dir, hit_bh, outside, status = self._exact.ray_trace_batch(

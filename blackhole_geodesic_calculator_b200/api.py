@@ -26,18 +26,21 @@ ESCAPED, CAPTURED, START_INSIDE_HOLE, LAMBDA_EXHAUSTED, STEP_FAILED, MISSED_SPHE
 STATUS_NAMES = {0: "ESCAPED", 1: "CAPTURED", 2: "START_INSIDE_HOLE", 3: "LAMBDA_EXHAUSTED", 4: "STEP_FAILED",
                 5: "MISSED_SPHERE"}
 MODES = {"parity": 0, "plane": 1}
+COORDS = {"schwarzschild": 0, "isotropic": 1}
 LAYOUT_SOA, LAYOUT_AOS = 0, 1
 
 
 def make_params(M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, max_step=math.inf, eps_horizon=0.01,
-                lambda_max=None, mode="parity", refill_threshold=0, image_width=0) -> BhgParams:
+                lambda_max=None, mode="parity", refill_threshold=0, image_width=0, coords="schwarzschild") -> BhgParams:
     if mode not in MODES:
         raise ValueError(f"mode must be one of {sorted(MODES)}, got {mode!r}")
+    if coords not in COORDS:
+        raise ValueError(f"coords must be one of {sorted(COORDS)}, got {coords!r}")
     if max_step is None or max_step == -1:  # the reference maps -1 to inf (RelativisticRenderEngine.py:59-60)
         max_step = math.inf
     return BhgParams(float(M), float(r_sphere), float(rtol), float(atol), float(max_step), float(eps_horizon),
                      0.0 if lambda_max is None else float(lambda_max), MODES[mode], int(refill_threshold),
-                     int(image_width), 0)
+                     int(image_width), COORDS[coords])
 
 
 def _is_torch(x):
@@ -46,9 +49,12 @@ def _is_torch(x):
 
 def trace(entry_pos, entry_dir, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, *, max_step=math.inf,
           eps_horizon=0.01, lambda_max=None, mode="parity", refill_threshold=0, image_width=0, device=0,
-          return_counters=False, disk=None, out=None, polyline=None):
+          return_counters=False, disk=None, out=None, polyline=None, coords="schwarzschild"):
     """Integrate N Schwarzschild null geodesics from sphere entry to exit or capture.
 
+    coords : chart of every position / direction / radius passed in and returned: "schwarzschild" (default; the
+        spherical chart of README.md:162-172 read as x = r sin th cos ph ...) or "isotropic" (the Cartesian chart of the
+        reference's older `SchwarzschildGeodesic` generation, the one README Fig. 5 / 6 are drawn in; include/bhgeo.h).
     entry_pos, entry_dir : [N,3] float64, BH-centred position and coordinate direction (numpy arrays on the
         host, or torch CUDA tensors, which are processed in place on their device and stream).
     image_width : optional scheduling hint — the rays are a row-major image of this width (the reference's
@@ -65,7 +71,7 @@ def trace(entry_pos, entry_dir, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, *, m
     int32 [2,N] array of (RK45 attempts, accepted steps), then disk_xy, then (poly_xyz, poly_count) if requested.
     """
     params = make_params(M, r_sphere, rtol, atol, max_step, eps_horizon, lambda_max, mode, refill_threshold,
-                         image_width)
+                         image_width, coords)
     if _is_torch(entry_pos):
         if polyline is not None:
             raise ValueError("polyline output is available for numpy inputs")

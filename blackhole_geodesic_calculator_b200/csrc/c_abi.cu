@@ -209,8 +209,9 @@ int validate(const bhg_params* p, long long n) {
         return fail(BHG_ERR_INVALID_ARGUMENT, "unknown mode %d", p->mode);
     if (p->refill_threshold < 0 || p->refill_threshold > 32)
         return fail(BHG_ERR_INVALID_ARGUMENT, "refill_threshold must be in 0..32");
-    if (p->image_width < 0 || p->reserved != 0)
-        return fail(BHG_ERR_INVALID_ARGUMENT, "image_width must be >= 0 and reserved must be 0");
+    if (p->image_width < 0) return fail(BHG_ERR_INVALID_ARGUMENT, "image_width must be >= 0");
+    if (p->coords != BHG_COORDS_SCHWARZSCHILD && p->coords != BHG_COORDS_ISOTROPIC)
+        return fail(BHG_ERR_INVALID_ARGUMENT, "unknown coords %d", p->coords);
     double lam = p->lambda_max;
     if (!(lam > 0.0) && !std::isfinite(p->r_sphere))
         return fail(BHG_ERR_INVALID_ARGUMENT, "lambda_max must be given when r_sphere is infinite");
@@ -255,6 +256,15 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
     a.rs = 2.0 * p->M;
     a.r_hor = a.rs + p->eps_horizon;
     a.r_sphere = p->r_sphere;
+    a.coords = p->coords;
+    // isotropic boundary: radii the caller states (sphere of influence, disk annulus) are isotropic radii; the
+    // integration runs on the Schwarzschild radius r = rho (1 + r_s / 4 rho)^2
+    auto schw_radius = [&](double rho) {
+        if (!(p->coords == BHG_COORDS_ISOTROPIC) || !std::isfinite(rho) || !(rho > 0.0)) return rho;
+        const double q = 1.0 + a.rs / (4.0 * rho);
+        return rho * q * q;
+    };
+    a.r_sphere = schw_radius(a.r_sphere);
     a.has_outer = std::isfinite(p->r_sphere) ? 1 : 0;
     a.rtol = p->rtol; a.atol = p->atol; a.max_step = p->max_step;
     a.lambda_max = p->lambda_max > 0.0 ? p->lambda_max : 10.0 * p->r_sphere;
@@ -266,7 +276,7 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
         if (v > 0) a.idle_budget = v;
     }
     a.tile_width = (image_width > 0 && image_width % 4 == 0 && n % (8LL * image_width) == 0 && !order) ? image_width : 0;
-    if (disk) { a.disk_r_in = ex->disk_r_in; a.disk_r_out = ex->disk_r_out; a.disk_xy = ex->disk_xy; }
+    if (disk) { a.disk_r_in = schw_radius(ex->disk_r_in); a.disk_r_out = schw_radius(ex->disk_r_out); a.disk_xy = ex->disk_xy; }
     if (poly) {
         a.poly_n = ex->poly_n;
         a.poly_dt = a.lambda_max / (ex->poly_n - 1);
@@ -371,7 +381,7 @@ void bhg_default_params(bhg_params* p) {
     p->mode = BHG_MODE_PARITY;
     p->refill_threshold = 0;
     p->image_width = 0;
-    p->reserved = 0;
+    p->coords = BHG_COORDS_SCHWARZSCHILD;
 }
 
 int bhg_trace_schwarzschild_f64(const double* in, const double* in_dir, double* out, double* out_dir,

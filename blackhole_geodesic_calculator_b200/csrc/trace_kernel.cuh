@@ -36,6 +36,7 @@ struct TraceArgs {
                            // since the last service reach this budget ("ski rental": idle until the waste equals
                            // the price of one service), which adapts to coherent and incoherent batches alike
     int tile_width;  // > 0: queue slots enumerate 4 x 8 pixel tiles of a row-major image of this width
+    int coords;      // 1: entry / exit states (and polyline, disk points) are given in ISOTROPIC Cartesian coordinates
     // DISK variant only: first crossing of the equatorial plane with disk_r_in <= r <= disk_r_out
     double disk_r_in, disk_r_out;
     double* disk_xy;  // [n][2], NaN = no hit
@@ -100,6 +101,54 @@ __device__ __forceinline__ bool load_ray(const TraceArgs& a, long long idx, doub
         }
     }
     return x[0] == x[0];  // false iff NaN
+}
+
+// ---- isotropic <-> Schwarzschild-coordinate boundary map (bhgeo.h BHG_COORDS_ISOTROPIC) --------------------------
+// The reference's older solver generation (`SchwarzschildGeodesic`, LimitedRelativisticRenderEngine.py:90,273) "uses
+// the Schwarzschild metric in cartesian coordinates" (README.md:174); README Fig. 5 / Fig. 6 are reproduced to the
+// pixel when those are the ISOTROPIC ones, rho with r = rho (1 + r_s / 4 rho)^2 (tests/golden/readme_fig5_fig6.npz).
+// The integration itself always runs in the spherical Schwarzschild chart of README.md:162-172; this is the
+// point map at the boundary.  Isotropic space is conformally flat, so the angle between a direction and the radial
+// unit vector is the metric angle: the radial component of the coordinate tangent scales by dr/drho = 1 - a^2, the
+// tangential one by r/rho = (1 + a)^2, a = r_s / (4 rho); directions are re-normalised (affine rescaling).
+__device__ __forceinline__ void iso_to_schw(double rs, double (&x)[3], double (&k)[3]) {
+    const double rho2 = fma(x[0], x[0], fma(x[1], x[1], x[2] * x[2]));
+    const double rho = sqrt(rho2);
+    const double a = 0.25 * rs / rho;
+    const double c = (-2.0 * a / (1.0 + a)) * fma(k[0], x[0], fma(k[1], x[1], k[2] * x[2])) / rho2;
+    double v[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) v[i] = fma(c, x[i], k[i]);
+    const double inv = rsqrt(fma(v[0], v[0], fma(v[1], v[1], v[2] * v[2])));
+    const double s = (1.0 + a) * (1.0 + a);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        k[i] = v[i] * inv;
+        x[i] *= s;
+    }
+}
+
+// isotropic radius of a Schwarzschild radius r >= rs (inside the horizon the chart ends: clamp the root at 0)
+__device__ __forceinline__ double iso_radius(double rs, double r) {
+    return 0.5 * (r - 0.5 * rs + sqrt(fmax(r * (r - rs), 0.0)));
+}
+
+__device__ __forceinline__ void schw_to_iso(double rs, double (&x)[3], double (&k)[3]) {
+    const double r2 = fma(x[0], x[0], fma(x[1], x[1], x[2] * x[2]));
+    const double r = sqrt(r2);
+    const double rho = iso_radius(rs, r);
+    const double a = 0.25 * rs / rho;
+    const double c = (2.0 * a / (1.0 - a)) * fma(k[0], x[0], fma(k[1], x[1], k[2] * x[2])) / r2;
+    double v[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) v[i] = fma(c, x[i], k[i]);
+    const double inv = rsqrt(fma(v[0], v[0], fma(v[1], v[1], v[2] * v[2])));
+    const double s = rho / r;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        k[i] = v[i] * inv;
+        x[i] *= s;
+    }
 }
 
 // outputs are AoS for IN_AOS (exit positions optional: a.out may be NULL), planes for IN_SOA
@@ -273,8 +322,9 @@ __device__ __forceinline__ bool disk_crossing(const TraceArgs& a, long long idx,
     double sp, cp;
     sincos_tab(ph, &sp, &cp);
     const double st = (((long long)m) & 1) ? -1.0 : 1.0;  // sin(pi/2 + m pi)
-    a.disk_xy[2 * idx] = r * st * cp;
-    a.disk_xy[2 * idx + 1] = r * st * sp;
+    const double ro = a.coords ? iso_radius(a.rs, r) : r;
+    a.disk_xy[2 * idx] = ro * st * cp;
+    a.disk_xy[2 * idx + 1] = ro * st * sp;
     return true;
 }
 
@@ -303,6 +353,7 @@ __device__ __forceinline__ int emit_polyline(const TraceArgs& a, long long idx, 
         sincos_tab(th, &st, &ct);
         sincos_tab(ph, &sp, &cp);
         double* o = a.poly_xyz + ((long long)idx * a.poly_n + pj) * 3;
+        if (a.coords) r = iso_radius(a.rs, r);
         o[0] = r * st * cp;
         o[1] = r * st * sp;
         o[2] = r * ct;
@@ -392,7 +443,10 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
                     t = fma(s, h, t);
                 }
                 double x0[3] = {0, 0, 0}, k0[3] = {0, 0, 0}, xo[3], ko[3];
-                if (NK == 3 || final_status == MISSED_SPHERE) load_ray<IN>(a, idx, x0, k0);
+                if (NK == 3 || final_status == MISSED_SPHERE) {
+                    const bool enters = load_ray<IN>(a, idx, x0, k0);
+                    if (a.coords && enters) iso_to_schw(a.rs, x0, k0);
+                }
                 if (final_status == START_INSIDE_HOLE) {
 #pragma unroll
                     for (int c = 0; c < 3; c++) xo[c] = ko[c] = __longlong_as_double(0x7ff8000000000000LL);
@@ -405,6 +459,7 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
                 } else {
                     if (!all_finite<NK>(k, x)) final_status = STEP_FAILED;
                     exit_state<NK>(k, x, x0, k0, xo, ko);
+                    if (a.coords) schw_to_iso(a.rs, xo, ko);
                 }
                 store_ray<IN>(a, idx, xo, ko, final_status, n_attempt, n_accept);
                 if constexpr (POLY) a.poly_count[idx] = pj;
@@ -427,6 +482,7 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
                         idx = slot_to_ray(a, slot);
                         double x0[3], k0[3];
                         const bool enters = load_ray<IN>(a, idx, x0, k0);
+                        if (a.coords && enters) iso_to_schw(a.rs, x0, k0);
                         n_attempt = 0;
                         n_accept = 0;
                         rejected = false;

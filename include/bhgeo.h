@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define BHG_VERSION 100 /* 0.1.0 */
+#define BHG_VERSION 110 /* 0.1.1: bhg_params.reserved became bhg_params.coords (same layout) */
 
 /* per-ray status codes written to `status` */
 enum bhg_status {
@@ -51,6 +51,21 @@ enum bhg_mode {
     BHG_MODE_PLANE = 1   /* optional: 6-state integration in each ray's conserved orbital plane           */
 };
 
+/* Chart of the Cartesian positions / directions at the boundary.  The integration itself always runs in the
+ * spherical Schwarzschild chart of README.md:162-172 (the current curvedpy generation: GeodesicIntegratorSchwarzschild
+ * + Conversions().convert_xyz_to_sph, RelativisticRenderEngine.py:134,289-291), x = r sin(th) cos(ph) etc.
+ * BHG_COORDS_ISOTROPIC maps entry states from, and results back to, the isotropic Cartesian chart
+ * (r = rho (1 + r_s / 4 rho)^2; radial tangent component x (1 - a^2), tangential x (1 + a)^2, a = r_s / 4 rho): the
+ * chart of the older solver generation `SchwarzschildGeodesic` ("uses the Schwarzschild metric in cartesian
+ * coordinates", README.md:174; LimitedRelativisticRenderEngine.py:90,273-278) - README Fig. 5 and Fig. 6, the only
+ * known answers the reference holds for this path, are reproduced to the pixel in this chart and in no other
+ * (tests/golden/readme_fig5_fig6.npz, tests/test_readme_figures.py).  eps_horizon stays an offset in the
+ * Schwarzschild radius; lambda_max counts affine length of the unit Schwarzschild-chart tangent. */
+enum bhg_coords {
+    BHG_COORDS_SCHWARZSCHILD = 0,
+    BHG_COORDS_ISOTROPIC = 1
+};
+
 /* memory layout of the ray buffers */
 enum bhg_layout {
     BHG_LAYOUT_SOA = 0, /* in: 6 planes of n doubles px,py,pz,dx,dy,dz; out: 6 planes px,py,pz,dx,dy,dz  */
@@ -77,7 +92,9 @@ typedef struct bhg_params {
                                  queue then hands every warp a 4 x 8 pixel tile instead of 32 pixels of one row.
                                  0 = no hint.  Ignored unless image_width % 4 == 0 and n % (8 image_width) == 0.
                                  Scheduling only: results are bit-identical with and without the hint.       */
-    int32_t reserved;         /* must be 0 */
+    int32_t coords;           /* enum bhg_coords: chart of every position / direction / radius that crosses this
+                                 boundary (entry and exit states, r_sphere, disk radii and hit points, polyline
+                                 samples).  0 = Schwarzschild coordinates (default).                          */
 } bhg_params;
 
 /* Fills *p with the reference defaults (M=1, r_sphere=60, rtol=1e-3, atol=1e-6, max_step=inf,

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_defaults():
     lib = _lib.load()
-    assert lib.bhg_version() == 100
+    assert lib.bhg_version() == 110
     p = _lib.BhgParams()
     lib.bhg_default_params(ctypes.byref(p))
     assert (p.M, p.r_sphere, p.rtol, p.atol, p.eps_horizon, p.mode) == (1.0, 60.0, 1e-3, 1e-6, 0.01, 0)

@@ -42,7 +42,7 @@ def test_rre_call_shape_per_ray_and_batch():
 def test_lim_call_shape_scaling_and_messages():
     from blackhole_geodesic_calculator_b200 import adapters, raygen
     from oracle import port
-    sw = adapters.SchwarzschildGeodesic(metric="schwarzschild")
+    sw = adapters.SchwarzschildGeodesic(metric="schwarzschild", coordinates="schwarzschild")
     ratio, r_obj = 30.0, 3.0            # a Blender sphere of radius 3 standing for 30 r_s (LIM.py:488)
     pos, d = raygen.config_bundle(24, 24, 1, fov=0.5, r_sphere=60.0)
     locs = pos / 60.0 * r_obj           # entry points on the Blender sphere, relative to its centre
@@ -82,13 +82,37 @@ def test_lim_call_shape_scaling_and_messages():
     x, y, z, el, ed, mes = sw.ray_trace(d[5], locs[5], ratio_obj_to_blackhole=ratio, curve_end=5.0)
     assert mes.get("error") == "Outside" and mes["hit_blackhole"] is False
     # the engine's `approx` branch (LIM.py:97-101,269): same attributes, same call, answered exactly
-    asw = adapters.ApproxSchwarzschildGeodesic(ratio_obj_to_blackhole=ratio, exit_tolerance=0.2)
+    asw = adapters.ApproxSchwarzschildGeodesic(ratio_obj_to_blackhole=ratio, exit_tolerance=0.2,
+                                               coordinates="schwarzschild")
     assert round(asw.exit_tolerance, 4) == 0.2 and round(asw.ratio_obj_to_blackhole, 4) == ratio
     a_loc, a_dir, a_mes = asw.generatedRayTracer(locs[5], d[5])
     assert np.array_equal(a_loc, end_loc[5]) and np.array_equal(a_dir, end_dir[5])
     assert a_mes["hit_blackhole"] == bool(hit_bh[5]) and "error" not in a_mes
     cap = int(np.nonzero(hit_bh)[0][0])
     assert asw.generatedRayTracer(locs[cap], d[cap])[2]["hit_blackhole"] is True
+    # default chart of this call shape: isotropic (README Fig. 5 / 6, tests/test_readme_figures.py) - the same rays
+    # read in that chart, against the oracle wrapped in the host-side maps (exit state, disk hit point, polyline)
+    from blackhole_geodesic_calculator_b200 import coords as C
+    swi = adapters.SchwarzschildGeodesic()
+    assert swi.coordinates == "isotropic"
+    end_loc, end_dir, hit_bh, outside, status, dxy = swi.ray_trace_batch(d, locs, ratio_obj_to_blackhole=ratio,
+                                                                         disk=(3.0, 12.0))
+    ps, ds = C.isotropic_to_schwarzschild(locs * (ratio / r_obj), d, 0.5)
+    R_s = float(C.schwarzschild_radius(ratio, 0.5))
+    o = port.trace(ps, ds, M=0.5, r_sphere=R_s, lambda_max=swi.approximateCurveEnd(ratio),
+                   disk=(float(C.schwarzschild_radius(3.0, 0.5)), float(C.schwarzschild_radius(12.0, 0.5))))
+    assert np.array_equal(status, o["status"]) and not outside.any()
+    esc = status == 0
+    pi_, di_ = C.schwarzschild_to_isotropic(o["exit_pos"][esc], o["exit_dir"][esc], 0.5)
+    assert np.abs(end_loc[esc] * (ratio / r_obj) - pi_).max() / ratio < 1e-6 and np.abs(end_dir[esc] - di_).max() < 1e-6
+    assert np.abs(np.linalg.norm(end_loc[esc], axis=1) - r_obj).max() < 1e-9
+    hit = np.isfinite(o["disk_xy"][:, 0])
+    assert np.array_equal(np.isfinite(dxy[:, 0]), hit) and hit.any()
+    rr = np.linalg.norm(o["disk_xy"][hit], axis=1)
+    assert np.abs(dxy[hit] - o["disk_xy"][hit] * (C.isotropic_radius(rr, 0.5) / rr)[:, None]).max() < 1e-6
+    x, y, z, el, ed, mes = swi.ray_trace(d[5], locs[5], ratio_obj_to_blackhole=ratio)
+    rr = np.sqrt(x * x + y * y + z * z)
+    assert abs(rr[0] - ratio) < 1e-9 and abs(rr[-1] - ratio) < 1e-6 and (rr <= ratio + 1e-9).all()
 
 
 def test_cam_call_shape():
