@@ -152,7 +152,7 @@ DeviceCtx g_ctx[kMaxDevices];
 
 template <int NK, int IN>
 int query_occupancy(int* out) {
-    BHG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, bhg::trace_kernel<NK, IN>, BHG_BLOCK, 0));
+    BHG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, bhg::trace_kernel<NK, IN, false, false, true>, BHG_BLOCK, 0));
     return 0;
 }
 
@@ -235,10 +235,36 @@ int convert_camera(const bhg_camera* cam, double r_sphere, bhg::Camera* out) {
     return 0;
 }
 
-// in_kind: bhg::IN_SOA / IN_AOS
+// The pre-pass (prepare_kernel) is the default; BHG_PREP=0 keeps the initialisation inside the trace kernel (A/B runs)
+bool prep_enabled() {
+    static const int v = [] {
+        const char* e = getenv("BHG_PREP");
+        return (e && atoi(e) == 0) ? 0 : 1;
+    }();
+    return v != 0;
+}
+
+template <int NK, int IN, bool DISK, bool POLY>
+void launch_trace_variant(bool prep, int blocks, cudaStream_t stream, const bhg::TraceArgs& a) {
+    if (prep) bhg::trace_kernel<NK, IN, DISK, POLY, true><<<blocks, BHG_BLOCK, 0, stream>>>(a);
+    else bhg::trace_kernel<NK, IN, DISK, POLY, false><<<blocks, BHG_BLOCK, 0, stream>>>(a);
+}
+
+template <int NK>
+void launch_prepare_variant(int in_kind, bool from_camera, int blocks, cudaStream_t stream, const bhg::TraceArgs& a,
+                            const bhg::Camera& cam, double* ray_pos, double* ray_dir) {
+    if (from_camera) bhg::prepare_kernel<NK, bhg::IN_CAMERA><<<blocks, 256, 0, stream>>>(a, cam, ray_pos, ray_dir);
+    else if (in_kind == bhg::IN_AOS) bhg::prepare_kernel<NK, bhg::IN_AOS><<<blocks, 256, 0, stream>>>(a, cam, nullptr, nullptr);
+    else if (in_kind == bhg::IN_AOS_F32) bhg::prepare_kernel<NK, bhg::IN_AOS_F32><<<blocks, 256, 0, stream>>>(a, cam, nullptr, nullptr);
+    else bhg::prepare_kernel<NK, bhg::IN_SOA><<<blocks, 256, 0, stream>>>(a, cam, nullptr, nullptr);
+}
+
+// in_kind: bhg::IN_SOA / IN_AOS / IN_AOS_F32.  `cam` != NULL: the rays come from the camera description (in / in_dir
+// are ignored; outputs are AoS) - parity mode needs no ray buffer at all, plane mode keeps one for its exit frame.
 int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* out, double* out_dir, int32_t* status,
                  int32_t* counters, const int32_t* order, long long n, int in_kind, int image_width,
-                 const bhg_params* p, cudaStream_t stream, const bhg_extras* ex = nullptr) {
+                 const bhg_params* p, cudaStream_t stream, const bhg_extras* ex = nullptr,
+                 const bhg::Camera* cam = nullptr) {
     if (n == 0) return 0;
     const bool disk = ex && ex->disk_xy && ex->disk_r_out > 0.0;
     const bool poly = ex && ex->poly_n >= 2 && ex->poly_xyz && ex->poly_count;
@@ -248,6 +274,8 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
         return fail(BHG_ERR_INVALID_ARGUMENT, "the disk-crossing event is available in parity mode only");
     if (disk && in_kind != bhg::IN_AOS)
         return fail(BHG_ERR_INVALID_ARGUMENT, "the disk-crossing event needs the float64 AOS layout");
+    if (disk && !(ex->disk_r_in >= 0.0 && ex->disk_r_in <= ex->disk_r_out))
+        return fail(BHG_ERR_INVALID_ARGUMENT, "the disk annulus needs 0 <= disk_r_in <= disk_r_out");
     bhg::TraceArgs a;
     memset(&a, 0, sizeof(a));
     a.in = in; a.in_dir = in_dir; a.out = out; a.out_dir = out_dir;
@@ -276,6 +304,14 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
         if (v > 0) a.idle_budget = v;
     }
     a.tile_width = (image_width > 0 && image_width % 4 == 0 && n % (8LL * image_width) == 0 && !order) ? image_width : 0;
+    if (a.tile_width > 0) {
+        // band = slot / d, d = 8 tile_width, for every slot < 2^31: (slot * ceil(2^(31+l) / d)) >> (31 + l), l = ceil(log2 d)
+        const unsigned long long d = 8ULL * (unsigned long long)a.tile_width;
+        int l = 0;
+        while ((1ULL << l) < d) l++;
+        a.tile_shift = 31 + l;
+        a.tile_magic = (unsigned long long)((((unsigned __int128)1 << a.tile_shift) + d - 1) / d);
+    }
     if (disk) { a.disk_r_in = schw_radius(ex->disk_r_in); a.disk_r_out = schw_radius(ex->disk_r_out); a.disk_xy = ex->disk_xy; }
     if (poly) {
         a.poly_n = ex->poly_n;
@@ -287,6 +323,27 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
     a.queue_head = c.queue_slots + slot;
     BHG_CUDA(cudaMemsetAsync(a.queue_head, 0, sizeof(unsigned long long), stream));
     const int mode = p->mode;
+    // ---- pre-pass: prepared rays in queue order (stream-ordered scratch)
+    const bool prep = prep_enabled() || cam != nullptr;
+    double* cam_rays = nullptr;
+    if (prep) {
+        const int planes = (mode == BHG_MODE_PARITY) ? 6 : 4;
+        BHG_CUDA(cudaMallocAsync((void**)&a.prep, (size_t)n * planes * sizeof(double2), stream));
+        if (cam && mode == BHG_MODE_PLANE) {  // the orbital-plane frame is rebuilt from the flat entry state at the exit
+            BHG_CUDA(cudaMallocAsync((void**)&cam_rays, (size_t)n * 48, stream));
+            a.in = cam_rays;
+            a.in_dir = cam_rays + 3 * n;
+        }
+        long long pb = (n + 255) / 256;
+        if (pb > c.sm_count * 16LL) pb = c.sm_count * 16LL;
+        bhg::Camera none;
+        memset(&none, 0, sizeof(none));
+        const bhg::Camera& cc = cam ? *cam : none;
+        if (mode == BHG_MODE_PARITY) launch_prepare_variant<4>(in_kind, cam != nullptr, (int)pb, stream, a, cc, nullptr, nullptr);
+        else launch_prepare_variant<3>(in_kind, cam != nullptr, (int)pb, stream, a, cc, cam_rays, cam_rays ? cam_rays + 3 * n : nullptr);
+        g_launches.fetch_add(1);
+        BHG_CUDA(cudaGetLastError());
+    }
     long long want_blocks = (n + BHG_BLOCK - 1) / BHG_BLOCK;
     long long max_blocks = (long long)c.sm_count * c.blocks_per_sm[mode][in_kind];
     if (const char* e = getenv("BHG_BLOCKS_PER_SM")) {  // tuning experiments: fewer resident warps
@@ -295,21 +352,23 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
     }
     int blocks = (int)(want_blocks < max_blocks ? want_blocks : max_blocks);
     if (poly) {
-        if (disk) bhg::trace_kernel<4, bhg::IN_AOS, true, true><<<blocks, BHG_BLOCK, 0, stream>>>(a);
-        else bhg::trace_kernel<4, bhg::IN_AOS, false, true><<<blocks, BHG_BLOCK, 0, stream>>>(a);
+        if (disk) launch_trace_variant<4, bhg::IN_AOS, true, true>(prep, blocks, stream, a);
+        else launch_trace_variant<4, bhg::IN_AOS, false, true>(prep, blocks, stream, a);
     } else if (disk) {
-        bhg::trace_kernel<4, bhg::IN_AOS, true><<<blocks, BHG_BLOCK, 0, stream>>>(a);
+        launch_trace_variant<4, bhg::IN_AOS, true, false>(prep, blocks, stream, a);
     } else if (mode == BHG_MODE_PARITY) {
-        if (in_kind == bhg::IN_AOS) bhg::trace_kernel<4, bhg::IN_AOS><<<blocks, BHG_BLOCK, 0, stream>>>(a);
-        else if (in_kind == bhg::IN_AOS_F32) bhg::trace_kernel<4, bhg::IN_AOS_F32><<<blocks, BHG_BLOCK, 0, stream>>>(a);
-        else bhg::trace_kernel<4, bhg::IN_SOA><<<blocks, BHG_BLOCK, 0, stream>>>(a);
+        if (in_kind == bhg::IN_AOS) launch_trace_variant<4, bhg::IN_AOS, false, false>(prep, blocks, stream, a);
+        else if (in_kind == bhg::IN_AOS_F32) launch_trace_variant<4, bhg::IN_AOS_F32, false, false>(prep, blocks, stream, a);
+        else launch_trace_variant<4, bhg::IN_SOA, false, false>(prep, blocks, stream, a);
     } else {
-        if (in_kind == bhg::IN_AOS) bhg::trace_kernel<3, bhg::IN_AOS><<<blocks, BHG_BLOCK, 0, stream>>>(a);
-        else if (in_kind == bhg::IN_AOS_F32) bhg::trace_kernel<3, bhg::IN_AOS_F32><<<blocks, BHG_BLOCK, 0, stream>>>(a);
-        else bhg::trace_kernel<3, bhg::IN_SOA><<<blocks, BHG_BLOCK, 0, stream>>>(a);
+        if (in_kind == bhg::IN_AOS) launch_trace_variant<3, bhg::IN_AOS, false, false>(prep, blocks, stream, a);
+        else if (in_kind == bhg::IN_AOS_F32) launch_trace_variant<3, bhg::IN_AOS_F32, false, false>(prep, blocks, stream, a);
+        else launch_trace_variant<3, bhg::IN_SOA, false, false>(prep, blocks, stream, a);
     }
     g_launches.fetch_add(1);
     BHG_CUDA(cudaGetLastError());
+    if (a.prep) cudaFreeAsync(a.prep, stream);
+    if (cam_rays) cudaFreeAsync(cam_rays, stream);
     return 0;
 }
 
@@ -662,16 +721,9 @@ int bhg_trace_camera_f64(const bhg_camera* cam, double* exit_pos, double* exit_d
     DeviceCtx* c;
     if ((rc = ensure_device(device, &c))) return rc;
     if (n == 0) return 0;
-    // generate (streaming kernel) then trace; the ray buffer is stream-ordered scratch
-    cudaStream_t s = (cudaStream_t)stream;
-    double* rays = nullptr;
-    BHG_CUDA(cudaMallocAsync((void**)&rays, (size_t)n * 48, s));
-    rc = launch_generate(*c, dc, n, rays, rays + 3 * n, nullptr, s);
-    if (!rc)
-        rc = launch_trace(*c, rays, rays + 3 * n, exit_pos, exit_dir, status, counters, nullptr, n, bhg::IN_AOS,
-                          camera_image_width(dc), params, s);
-    cudaFreeAsync(rays, s);
-    return rc;
+    // the pre-pass generates each primary ray from the camera description and prepares it in one go: no ray buffer
+    return launch_trace(*c, nullptr, nullptr, exit_pos, exit_dir, status, counters, nullptr, n, bhg::IN_AOS,
+                        camera_image_width(dc), params, (cudaStream_t)stream, nullptr, &dc);
 }
 
 int bhg_trace_camera_f64_host(const bhg_camera* cam, double* exit_pos, double* exit_dir, int32_t* status,
@@ -705,9 +757,8 @@ int bhg_trace_camera_f64_host(const bhg_camera* cam, double* exit_pos, double* e
         bhg::Camera cc = dc;
         cc.first_ray = dc.first_ray + b;
         int32_t* cnt_chunk = counters ? d_cnt + 2 * b : nullptr;
-        if ((rc = launch_generate(*c, cc, m, d_pin + 3 * b, d_din + 3 * b, nullptr, s))) return rc;
-        rc = launch_trace(*c, d_pin + 3 * b, d_din + 3 * b, exit_pos ? d_pout + 3 * b : nullptr, d_dout + 3 * b,
-                          d_status + b, cnt_chunk, nullptr, m, bhg::IN_AOS, camera_image_width(cc), params, s);
+        rc = launch_trace(*c, nullptr, nullptr, exit_pos ? d_pout + 3 * b : nullptr, d_dout + 3 * b,
+                          d_status + b, cnt_chunk, nullptr, m, bhg::IN_AOS, camera_image_width(cc), params, s, nullptr, &cc);
         if (rc) return rc;
         if (exit_pos) BHG_CUDA(cudaMemcpyAsync(exit_pos + 3 * b, d_pout + 3 * b, (size_t)m * 24, cudaMemcpyDeviceToHost, s));
         BHG_CUDA(cudaMemcpyAsync(exit_dir + 3 * b, d_dout + 3 * b, (size_t)m * 24, cudaMemcpyDeviceToHost, s));
@@ -764,9 +815,8 @@ int bhg_trace_camera_sky_host(const bhg_camera* cam, float* uv, int32_t* status,
         cudaStream_t s = c->streams[si];
         bhg::Camera cc = dc;
         cc.first_ray = dc.first_ray + b;
-        if ((rc = launch_generate(*c, cc, m, d_pin + 3 * b, d_din + 3 * b, nullptr, s))) return rc;
-        rc = launch_trace(*c, d_pin + 3 * b, d_din + 3 * b, nullptr, d_dout + 3 * b, d_status + b, nullptr, nullptr, m,
-                          bhg::IN_AOS, camera_image_width(cc), params, s);
+        rc = launch_trace(*c, nullptr, nullptr, nullptr, d_dout + 3 * b, d_status + b, nullptr, nullptr, m,
+                          bhg::IN_AOS, camera_image_width(cc), params, s, nullptr, &cc);
         if (rc) return rc;
         long long blocks = (m + 255) / 256;
         if (blocks > c->sm_count * 16LL) blocks = c->sm_count * 16LL;

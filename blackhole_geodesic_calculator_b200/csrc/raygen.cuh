@@ -76,6 +76,13 @@ __device__ __forceinline__ bool camera_ray(const Camera& c, long long idx, doubl
                                 __dmul_rn(d[2], c.origin[2]));
     const double oo = __dadd_rn(__dadd_rn(__dmul_rn(c.origin[0], c.origin[0]), __dmul_rn(c.origin[1], c.origin[1])),
                                 __dmul_rn(c.origin[2], c.origin[2]));
+    // camera inside the sphere of influence (the RRE / CAM engines put it there: RelativisticRenderEngine.py:278,
+    // RelativisticRenderEngineCamEdition.py:212): the ray starts at the camera itself
+    if (oo < __dmul_rn(c.r_sphere, c.r_sphere)) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) p[i] = c.origin[i];
+        return true;
+    }
     const double disc = __dadd_rn(__dmul_rn(od, od), -__dadd_rn(oo, -__dmul_rn(c.r_sphere, c.r_sphere)));
     if (!(disc >= 0.0) || !(od < 0.0)) return false;
     const double s = __dadd_rn(-od, -sqrt(disc));

@@ -37,6 +37,12 @@ struct TraceArgs {
                            // the price of one service), which adapts to coherent and incoherent batches alike
     int tile_width;  // > 0: queue slots enumerate 4 x 8 pixel tiles of a row-major image of this width
     int coords;      // 1: entry / exit states (and polyline, disk points) are given in ISOTROPIC Cartesian coordinates
+    // band = slot / (8 tile_width) without a 64-bit division: (slot * tile_magic) >> tile_shift, exact for slot < 2^31
+    unsigned long long tile_magic;
+    int tile_shift;
+    // Prepared rays (pre-pass, prepare_kernel): initial spherical state, f0 and Hairer's first step of every ray in
+    // QUEUE order as planes of double2 (coalesced 16-byte loads on refill); NULL = initialise inside the trace kernel
+    double2* prep;
     // DISK variant only: first crossing of the equatorial plane with disk_r_in <= r <= disk_r_out
     double disk_r_in, disk_r_out;
     double* disk_xy;  // [n][2], NaN = no hit
@@ -63,7 +69,7 @@ __device__ __forceinline__ long long slot_to_ray(const TraceArgs& a, long long s
         // tiles 4 pixels wide x 8 tall (bands of 8 image rows); measured against 8 wide x 4 tall: config 2
         // 3.463 vs 3.504 ms, config 3 equal (profiles/r1m_experiments.txt)
         const long long band_sz = 8LL * a.tile_width;
-        const long long band = slot / band_sz;
+        const long long band = (long long)(((unsigned long long)slot * a.tile_magic) >> a.tile_shift);
         const int t = (int)(slot - band * band_sz);
         const int tile = t >> 5, l = t & 31;
         return band * band_sz + (long long)(l >> 2) * a.tile_width + (tile << 2) + (l & 3);
@@ -289,12 +295,17 @@ __device__ __forceinline__ void exit_state<3>(const double (&k)[3], const double
     }
 }
 
+// every component finite?  0 * v is NaN exactly for v = +-inf / NaN: two short FMA chains and one compare instead of
+// 2 NK exponent tests (the service path is latency-bound: profiles/r2a_instruction_budget_by_source.txt)
 template <int NK>
 __device__ __forceinline__ bool all_finite(const double (&k)[NK], const double (&x)[NK]) {
-    bool ok = true;
+    double a = 0.0, b = 0.0;
 #pragma unroll
-    for (int i = 0; i < NK; i++) ok = ok && isfinite(k[i]) && isfinite(x[i]);
-    return ok;
+    for (int i = 0; i < NK; i++) {
+        a = fma(k[i], 0.0, a);
+        b = fma(x[i], 0.0, b);
+    }
+    return (a + b) == 0.0;
 }
 
 // Equatorial-plane crossing inside the step [0, s_max] of the dense output (non-terminal event):
@@ -362,6 +373,92 @@ __device__ __forceinline__ int emit_polyline(const TraceArgs& a, long long idx, 
     return pj;
 }
 
+// ---- prepared rays -------------------------------------------------------------------------------------------------
+// Record of one ray after the pre-pass, NK = 4: {k_t, k_r, k_th, k_ph, r, th, ph, K0[4], h0} = 12 doubles = 6 double2
+// planes; NK = 3: {k_t, k_r, k_ph, r, K0[3], h0} = 8 doubles = 4 planes (t = 0, plane phi = 0).  h0 < 0 encodes the rays
+// that are not integrated: -1 START_INSIDE_HOLE, -2 STEP_FAILED (singular entry), -3 MISSED_SPHERE (k holds the flat
+// direction).
+template <int NK>
+struct Prep {
+    static constexpr int PL = (NK == 4) ? 6 : 4;
+    __device__ __forceinline__ static void pack(const double (&k)[NK], const double (&x)[NK], const double (&K0)[NK],
+                                                double h0, double (&v)[2 * PL]) {
+        int j = 0;
+#pragma unroll
+        for (int i = 0; i < NK; i++) v[j++] = k[i];
+#pragma unroll
+        for (int i = 1; i < (NK == 4 ? 4 : 2); i++) v[j++] = x[i];
+#pragma unroll
+        for (int i = 0; i < NK; i++) v[j++] = K0[i];
+        v[j] = h0;
+    }
+    __device__ __forceinline__ static double unpack(const double (&v)[2 * PL], double (&k)[NK], double (&x)[NK],
+                                                    double (&K0)[NK]) {
+        int j = 0;
+#pragma unroll
+        for (int i = 0; i < NK; i++) k[i] = v[j++];
+        x[0] = 0.0;
+#pragma unroll
+        for (int i = 1; i < NK; i++) x[i] = (NK == 4 || i < 2) ? v[j++] : 0.0;
+#pragma unroll
+        for (int i = 0; i < NK; i++) K0[i] = v[j++];
+        return v[j];
+    }
+};
+
+constexpr int IN_CAMERA = 3;  // prepare_kernel only: rays come from the camera description, not from memory
+
+// Pre-pass: entry conversion (xyz -> spherical position and tangent, null k_t: RelativisticRenderEngine.py:289-291,134),
+// f0 and Hairer's initial step (scipy/_ivp/rk.py:94-103, common.py:68-134) for every ray, written in queue order.
+// In the trace kernel this work runs once per warp-service on a latency-bound dependency chain (~1700 instructions,
+// 12 % of all warp time); here it is throughput-bound streaming work for 2048 resident threads per SM.
+template <int NK, int IN>
+__global__ void __launch_bounds__(256) prepare_kernel(const TraceArgs a, const Camera cam, double* __restrict__ ray_pos,
+                                                      double* __restrict__ ray_dir) {
+    constexpr int PL = Prep<NK>::PL;
+    for (long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x; slot < a.n;
+         slot += (long long)gridDim.x * blockDim.x) {
+        const long long idx = slot_to_ray(a, slot);
+        double x0[3], k0[3];
+        bool enters;
+        if (IN == IN_CAMERA) {
+            enters = camera_ray(cam, idx, x0, k0);
+            if (ray_pos) {  // plane mode rebuilds its orbital frame from the flat entry state at the exit
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    ray_pos[3 * idx + c] = enters ? x0[c] : __longlong_as_double(0x7ff8000000000000LL);
+                    ray_dir[3 * idx + c] = k0[c];
+                }
+            }
+        } else {
+            enters = load_ray<(IN == IN_CAMERA ? IN_AOS : IN)>(a, idx, x0, k0);
+        }
+        double k[NK], x[NK], K0[NK], h0;
+#pragma unroll
+        for (int i = 0; i < NK; i++) k[i] = x[i] = K0[i] = 0.0;
+        if (!enters) {
+            h0 = -3.0;
+#pragma unroll
+            for (int c = 0; c < 3; c++) k[c] = k0[c];
+        } else {
+            if (a.coords) iso_to_schw(a.rs, x0, k0);
+            if (!init_state<NK>(x0, k0, a.rs, a.r_hor, k, x)) {
+                h0 = -1.0;
+            } else if (!all_finite<NK>(k, x)) {
+                h0 = -2.0;
+            } else {
+                Rhs<NK>::eval(k, x, a.rs, K0);
+                h0 = initial_step<NK>(k, x, K0, a.rs, a.rtol, a.atol, a.lambda_max, a.max_step);
+                if (h0 < 0.0) h0 = 0.0;  // cannot happen (steps are non-negative); keeps the status encoding unambiguous
+            }
+        }
+        double v[2 * PL];
+        Prep<NK>::pack(k, x, K0, h0, v);
+#pragma unroll
+        for (int pl = 0; pl < PL; pl++) a.prep[(long long)pl * a.n + slot] = make_double2(v[2 * pl], v[2 * pl + 1]);
+    }
+}
+
 #ifndef BHG_MIN_BLOCKS
 #define BHG_MIN_BLOCKS 1
 #endif
@@ -369,7 +466,7 @@ __device__ __forceinline__ int emit_polyline(const TraceArgs& a, long long idx, 
 #define BHG_BLOCK 512
 #endif
 
-template <int NK, int IN, bool DISK = false, bool POLY = false>
+template <int NK, int IN, bool DISK = false, bool POLY = false, bool PREP = false>
 __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const TraceArgs a) {
     static_assert(!(DISK || POLY) || NK == 4, "disk event and polyline are defined for the spherical (parity) state");
     constexpr int IR = 1;  // index of r in x
@@ -422,11 +519,18 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
                     const double h = h_abs;
                     double q[4];
                     dense_coeffs_x(k[IR], K[0][IR], K[1][IR], K[2][IR], K[3][IR], K[4][IR], K[5][IR], h, q);
-                    double s_h = 2.0, s_e = 2.0;
-                    if (state == PEND_H || state == PEND_HE) s_h = event_root(q, x[IR], h, a.r_hor);
-                    if (state == PEND_E || state == PEND_HE) s_e = event_root(q, x[IR], h, a.r_sphere);
-                    const double s = fmin(s_h, s_e);  // earliest terminal event (ivp.py:117-126)
-                    final_status = (s_h <= s_e) ? CAPTURED : ESCAPED;
+                    // one root search per lane: the horizon for PEND_H / PEND_HE, the sphere for PEND_E; only a step
+                    // that crossed BOTH surfaces (never seen outside tests) searches the second one as well
+                    const bool first_is_h = (state != PEND_E);
+                    double s = event_root(q, x[IR], h, first_is_h ? a.r_hor : a.r_sphere);
+                    final_status = first_is_h ? CAPTURED : ESCAPED;
+                    if (state == PEND_HE) {
+                        const double s_e = event_root(q, x[IR], h, a.r_sphere);
+                        if (s_e < s) {  // earliest terminal event wins, the horizon on a tie (ivp.py:117-126)
+                            s = s_e;
+                            final_status = ESCAPED;
+                        }
+                    }
                     if constexpr (DISK) {  // crossings before the terminal root still count
                         if (!disk_hit) disk_hit = disk_crossing(a, idx, k, x, K, h, s);
                     }
@@ -443,9 +547,13 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
                     t = fma(s, h, t);
                 }
                 double x0[3] = {0, 0, 0}, k0[3] = {0, 0, 0}, xo[3], ko[3];
-                if (NK == 3 || final_status == MISSED_SPHERE) {
+                if (NK == 3 || (!PREP && final_status == MISSED_SPHERE)) {
                     const bool enters = load_ray<IN>(a, idx, x0, k0);
                     if (a.coords && enters) iso_to_schw(a.rs, x0, k0);
+                }
+                if (PREP && final_status == MISSED_SPHERE) {  // the record carries the flat direction
+#pragma unroll
+                    for (int c = 0; c < 3; c++) k0[c] = k[c];
                 }
                 if (final_status == START_INSIDE_HOLE) {
 #pragma unroll
@@ -480,25 +588,41 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
                     const long long slot = (long long)base + __popc(idle & lt_mask);
                     if (slot < a.n) {
                         idx = slot_to_ray(a, slot);
-                        double x0[3], k0[3];
-                        const bool enters = load_ray<IN>(a, idx, x0, k0);
-                        if (a.coords && enters) iso_to_schw(a.rs, x0, k0);
                         n_attempt = 0;
                         n_accept = 0;
                         rejected = false;
                         disk_hit = false;
                         pj = 0;
                         t = 0.0;
-                        if (!enters) {
-                            state = MISSED_SPHERE;
-                        } else if (!init_state<NK>(x0, k0, a.rs, a.r_hor, k, x)) {
-                            state = START_INSIDE_HOLE;
-                        } else if (!all_finite<NK>(k, x)) {
-                            state = STEP_FAILED;  // singular entry (on the polar axis): scipy refuses such a y0
+                        if constexpr (PREP) {
+                            constexpr int PL = Prep<NK>::PL;
+                            double v[2 * PL];
+#pragma unroll
+                            for (int pl = 0; pl < PL; pl++) {
+                                const double2 w = __ldg(a.prep + (long long)pl * a.n + slot);
+                                v[2 * pl] = w.x;
+                                v[2 * pl + 1] = w.y;
+                            }
+                            const double h0 = Prep<NK>::unpack(v, k, x, K[0]);
+                            h_abs = h0;
+                            state = !(h0 < 0.0) ? LANE_RUNNING
+                                                : (h0 == -1.0 ? (int)START_INSIDE_HOLE
+                                                              : (h0 == -2.0 ? (int)STEP_FAILED : MISSED_SPHERE));
                         } else {
-                            Rhs<NK>::eval(k, x, a.rs, K[0]);  // f0 (rk.py:94)
-                            h_abs = initial_step<NK>(k, x, K[0], a.rs, a.rtol, a.atol, t_bound, a.max_step);
-                            state = LANE_RUNNING;
+                            double x0[3], k0[3];
+                            const bool enters = load_ray<IN>(a, idx, x0, k0);
+                            if (a.coords && enters) iso_to_schw(a.rs, x0, k0);
+                            if (!enters) {
+                                state = MISSED_SPHERE;
+                            } else if (!init_state<NK>(x0, k0, a.rs, a.r_hor, k, x)) {
+                                state = START_INSIDE_HOLE;
+                            } else if (!all_finite<NK>(k, x)) {
+                                state = STEP_FAILED;  // singular entry (on the polar axis): scipy refuses such a y0
+                            } else {
+                                Rhs<NK>::eval(k, x, a.rs, K[0]);  // f0 (rk.py:94)
+                                h_abs = initial_step<NK>(k, x, K[0], a.rs, a.rtol, a.atol, t_bound, a.max_step);
+                                state = LANE_RUNNING;
+                            }
                         }
                     }
                 }

@@ -133,10 +133,14 @@ def camera_rays(width, height, samples=1, fov_x=CFG_FOV, fov_y=CFG_FOV, rotation
 def sphere_entry(origin, directions, r_sphere, center=(0.0, 0.0, 0.0)):
     """First intersection of flat rays with the sphere of influence, relative to its centre.
 
-    Returns (entry_pos[N,3], hit_mask[N]); rows with hit_mask False are NaN.
+    Returns (entry_pos[N,3], hit_mask[N]); rows with hit_mask False are NaN.  A camera INSIDE the sphere (where the
+    RRE / CAM engines put it, RelativisticRenderEngine.py:278, RelativisticRenderEngineCamEdition.py:212) starts every
+    ray at the camera itself.
     """
     o = np.asarray(origin, dtype=np.float64) - np.asarray(center, dtype=np.float64)
     d = np.asarray(directions, dtype=np.float64)
+    if o @ o < r_sphere * r_sphere:
+        return np.broadcast_to(o, d.shape).copy(), np.ones(d.shape[0], dtype=bool)
     od = d @ o
     disc = od * od - (o @ o - r_sphere * r_sphere)
     hit = (disc >= 0.0) & (od < 0.0)

@@ -1,0 +1,116 @@
+"""Register-read cost model of the RK45 attempt, per source line (needs -lineinfo).
+
+Measured on B200 (profiles/r2e_regread.txt): an FP64 instruction occupies its sub-partition for max(2, R) cycles, R =
+number of distinct 64-bit REGISTER source operands not served by the operand-reuse cache (uniform registers, constant
+bank operands and immediates are free); with R = 2 nothing else issues in those two cycles, with R <= 1 one ALU
+instruction hides in the second cycle.  Every other instruction costs one cycle.  The model brackets the measured
+1532 cycles per warp-attempt per scheduler of the round-1 loop ([1441, 1566]).
+
+    python scripts/sass_cost.py [--kernel 4,1,0,0,1] [--top 40]
+"""
+import argparse, collections, glob, os, re, subprocess, sys, tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FP64 = ("DFMA", "DMUL", "DADD", "DSETP", "DMNMX")
+INS = re.compile(r"^\s*/\*([0-9a-f]{4,})\*/\s+(.*?) ;")
+LOC = re.compile(r'//## File "([^"]+)", line (\d+)(?: inlined at "([^"]+)", line (\d+))?')
+
+
+def disassemble(lib):
+    tmp = tempfile.mkdtemp(prefix="bhg_sass_")
+    subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, check=True, capture_output=True)
+    cubin = glob.glob(os.path.join(tmp, "*.cubin"))[0]
+    return subprocess.run(["nvdisasm", "-gi", "-c", cubin], capture_output=True, text=True).stdout
+
+
+def reg_operands(txt, prev_reuse):
+    op = txt.split()[0]
+    ops = [o.strip() for o in txt[len(op):].split(",")]
+    base = op.split(".")[0]
+    srcs = ops[2:] if base == "DSETP" else ops[1:]
+    regs, new_reuse = [], {}
+    for slot, o in enumerate(srcs):
+        o2 = o.replace("|", "").lstrip("-").lstrip("~")
+        mm = re.match(r"^(R\d+)(\.reuse)?$", o2)
+        if mm:
+            r = mm.group(1)
+            if mm.group(2):
+                new_reuse[slot] = r
+            if prev_reuse.get(slot) == r:
+                continue
+            regs.append(r)
+    return len(set(regs)), new_reuse
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--lib", default=os.path.join(ROOT, "blackhole_geodesic_calculator_b200", "lib", "libbhgeo.so"))
+    ap.add_argument("--kernel", default="4,1,0,0,1")
+    ap.add_argument("--top", type=int, default=60)
+    ap.add_argument("--first-line", type=int, default=0, help="first line of the attempt in trace_kernel.cuh (auto)")
+    a = ap.parse_args()
+    t = [int(v) for v in a.kernel.split(",")]
+    name = "_ZN3bhg12trace_kernelILi%dELi%dELb%dELb%dELb%dEEEvNS_9TraceArgsE" % tuple(t)
+    txt = disassemble(a.lib)
+    start = txt.index(".text." + name + ":")
+    end = txt.find("//--------------------- .text.", start)
+    body = txt[start:end if end > 0 else None].splitlines()
+    src = {}
+    for f in ("trace_kernel.cuh", "geodesic_core.cuh"):
+        with open(os.path.join(ROOT, "blackhole_geodesic_calculator_b200", "csrc", f)) as fh:
+            src[f] = fh.read().splitlines()
+    first = a.first_line
+    if not first:
+        for i, l in enumerate(src["trace_kernel.cuh"]):
+            if "one RK45 attempt (rk.py:111-176)" in l:
+                first = i
+    chain, pending, prev_reuse = [], [], {}
+    per = collections.defaultdict(lambda: [0, 0, 0, 0])  # fp64 instrs, fp64 cycles, shadows, other instrs
+    tot = [0, 0, 0, 0]
+    hist = collections.Counter()
+    for ln in body:
+        m = LOC.search(ln)
+        if m:
+            if not pending or pending[-1][1] is None:
+                pending = []
+            pending.append(((os.path.basename(m.group(1)), int(m.group(2))),
+                            (os.path.basename(m.group(3)), int(m.group(4))) if m.group(3) else None))
+            continue
+        mi = INS.match(ln)
+        if not mi:
+            continue
+        if pending:
+            chain = [pending[0][0]] + [p[1] for p in pending if p[1]]
+            pending = []
+        itxt = re.sub(r"^@!?U?P\d+\s+", "", mi.group(2))
+        op = itxt.split()[0]
+        in_attempt = any(f == "trace_kernel.cuh" and l >= first for f, l in chain)
+        nreg, prev_reuse = reg_operands(itxt, prev_reuse)
+        if not in_attempt:
+            continue
+        key = None
+        for f, l in chain:  # innermost frame in our own sources
+            if f in src:
+                key = "%s:%d %s" % (f[:5], l, src[f][l - 1].strip()[:80])
+                break
+        key = key or "(library)"
+        v = per[key]
+        if op.startswith(FP64):
+            c = max(2, nreg)
+            v[0] += 1; v[1] += c; v[2] += nreg <= 1
+            tot[0] += 1; tot[1] += c; tot[2] += nreg <= 1
+            hist[(op.split(".")[0], nreg)] += 1
+        else:
+            v[3] += 1; tot[3] += 1
+            hist[(op.split(".")[0], -1)] += 1
+    print("attempt: FP64 instrs %d, FP64 cycles %d, shadow slots %d, other instrs %d -> cycles in [%d, %d]" %
+          (tot[0], tot[1], tot[2], tot[3], tot[1] + max(0, tot[3] - tot[2]), tot[1] + tot[3]))
+    print("FP64 by register operands:", sorted((k, v) for k, v in hist.items() if k[1] >= 0))
+    print("other:", sorted(((k[0], v) for k, v in hist.items() if k[1] < 0), key=lambda kv: -kv[1]))
+    print("%5s %5s %5s %5s  line" % ("fp64", "cyc", "shdw", "other"))
+    for k, v in sorted(per.items(), key=lambda kv: -(kv[1][1] + kv[1][3]))[:a.top]:
+        print("%5d %5d %5d %5d  %s" % (v[0], v[1], v[2], v[3], k))
+
+
+if __name__ == "__main__":
+    sys.exit(main())

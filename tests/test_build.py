@@ -33,7 +33,7 @@ def test_trace_kernel_variants_fit_the_launch_design():
 
 
 def test_hot_kernel_uses_the_fp64_pipe_without_slow_paths():
-    sass = _run("-sass", "-fun", "_ZN3bhg12trace_kernelILi4ELi1ELb0ELb0EEEvNS_9TraceArgsE")
+    sass = _run("-sass", "-fun", "_ZN3bhg12trace_kernelILi4ELi1ELb0ELb0ELb1EEEvNS_9TraceArgsE")
     ops = re.findall(r"^\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\w+\s+)?([A-Z0-9_.]+)", sass, flags=re.M)
     count = lambda prefix: sum(o.startswith(prefix) for o in ops)
     assert count("DFMA") > 600 and count("DMUL") > 300 and count("MUFU.RCP64H") >= 8
