@@ -124,6 +124,12 @@ __device__ __forceinline__ double inv_tenth_root(double a) {
 // measured the same, profiles/r1m_experiments.txt).
 __device__ __forceinline__ double abs_max(double a, double b) { return fmax(fabs(a), fabs(b)); }
 
+// The operand of larger magnitude, sign kept (the caller applies |.| as an operand modifier of its FMA): one compare and
+// one 64-bit select.  fmax()'s NaN handling costs five more ALU instructions per call, each of which needs two register
+// reads and therefore a cycle of its own (profiles/r2e_regread2.txt).  A NaN b is returned (NaN scale -> the step is
+// rejected); a is an accepted state and never NaN.
+__device__ __forceinline__ double larger_mag(double a, double b) { return fabs(a) > fabs(b) ? a : b; }
+
 // a^(1/5) for a in [1e-30, 1e30] (initial-step heuristic): Newton on x^-5 = a for the inverse root, then
 // a * x^4.  Float seed 1e-5 -> two steps -> 1e-18.
 __device__ __forceinline__ double fifth_root(double a) {
@@ -164,7 +170,7 @@ __device__ __forceinline__ void sincos_tab(double th, double* s, double* c) {
     pc = fma(z, pc, TAB(T_C2));
     ps = fma(z, ps, TAB(T_S1));
     pc = fma(z, pc, TAB(T_C1));
-    const double sr = fma(z * r, ps, r);                 // sin(r) = r + r^3 S(z)
+    const double sr = fma(r, z * ps, r);                 // sin(r) = r + r (z S(z)): two distinct register operands
     const double cr = fma(z, fma(z, pc, -0.5), 1.0);     // cos(r) = 1 - z/2 + z^2 C(z)
     const double a = (n & 1) ? cr : sr;
     const double b = (n & 1) ? sr : cr;
@@ -198,15 +204,17 @@ struct Rhs<4> {
         const double i_rrm = inv * s;         // 1 / (r (r - rs))
         const double i_r = i_rrm * rm;        // 1 / r
         const double hA = (0.5 * rs) * i_rrm; // rs / (2 r (r - rs))   (0.5 rs is loop-invariant)
-        const double kph2s = (kph * kph) * s;
-        const double ang = fma(kph2s, s, kth * kth);  // k_th^2 + k_ph^2 sin^2
-        const double q = rm * i_r;                    // (r - rs) / r
-        const double w = (hA * q) * q;                // rs (r - rs) / (2 r^3)
+        // Forms chosen for the register-read budget (profiles/r2e_regread2.txt): an FP64 instruction costs
+        // max(2, distinct register operands) cycles, so squares (one operand) and products with constants are cheap and
+        // three-variable FMAs are dear.
+        const double u = (rm * i_r) * kt;             // (1 - rs/r) k_t
+        const double d = fma(-u, u, kr * kr);         // k_r^2 - (1 - rs/r)^2 k_t^2
+        const double kphs = kph * s;
+        const double ang = fma(kphs, kphs, kth * kth);  // k_th^2 + k_ph^2 sin^2
         const double kr_r = kr * i_r;
-        const double hAkr = hA * kr;
-        f[0] = (-2.0 * hAkr) * kt;
-        f[1] = fma(hAkr, kr, fma(-w * kt, kt, rm * ang));
-        f[2] = fma(kr_r * kth, -2.0, kph2s * c);
+        f[0] = ((-2.0 * hA) * kr) * kt;
+        f[1] = fma(hA, d, rm * ang);
+        f[2] = fma(kr_r * kth, -2.0, (kphs * kph) * c);
         f[3] = (-2.0 * kph) * fma(kth, c * i_s, kr_r);
     }
 };
@@ -347,8 +355,8 @@ __device__ __forceinline__ double rk45_attempt(const double (&k)[NK], const doub
         g = fma(TAB(EA4), K[3][i], g);
         g = fma(TAB(EA5), K[4][i], g);
         ex[i] = fma(TAB(EA6), K[5][i], g);         // error / h^2 (position half)
-        sk[i] = fma(abs_max(k[i], kn[i]), rtol, atol);
-        sx[i] = fma(abs_max(x[i], xn[i]), rtol, atol);
+        sk[i] = fma(fabs(larger_mag(k[i], kn[i])), rtol, atol);
+        sx[i] = fma(fabs(larger_mag(x[i], xn[i])), rtol, atol);
     }
     // one reciprocal per group of four scales (two momentum/position pairs); scales are >= atol so the
     // products neither overflow nor underflow.  sum (e_i/scale_i)^2 = h^2 (S_k + h^2 S_x): h is applied once.

@@ -65,7 +65,7 @@ def main():
             if "one RK45 attempt (rk.py:111-176)" in l:
                 first = i
     chain, pending, prev_reuse = [], [], {}
-    per = collections.defaultdict(lambda: [0, 0, 0, 0])  # fp64 instrs, fp64 cycles, shadows, other instrs
+    per = collections.defaultdict(lambda: [0, 0, 0, 0, 0])  # fp64 instrs, fp64 cycles, shadows, other instrs, 3-reg
     tot = [0, 0, 0, 0]
     hist = collections.Counter()
     for ln in body:
@@ -97,7 +97,7 @@ def main():
         v = per[key]
         if op.startswith(FP64):
             c = max(2, nreg)
-            v[0] += 1; v[1] += c; v[2] += nreg <= 1
+            v[0] += 1; v[1] += c; v[2] += nreg <= 1; v[4] += nreg >= 3
             tot[0] += 1; tot[1] += c; tot[2] += nreg <= 1
             hist[(op.split(".")[0], nreg)] += 1
         else:
@@ -107,9 +107,9 @@ def main():
           (tot[0], tot[1], tot[2], tot[3], tot[1] + max(0, tot[3] - tot[2]), tot[1] + tot[3]))
     print("FP64 by register operands:", sorted((k, v) for k, v in hist.items() if k[1] >= 0))
     print("other:", sorted(((k[0], v) for k, v in hist.items() if k[1] < 0), key=lambda kv: -kv[1]))
-    print("%5s %5s %5s %5s  line" % ("fp64", "cyc", "shdw", "other"))
+    print("%5s %5s %5s %5s %5s  line" % ("fp64", "cyc", "shdw", "other", "3reg"))
     for k, v in sorted(per.items(), key=lambda kv: -(kv[1][1] + kv[1][3]))[:a.top]:
-        print("%5d %5d %5d %5d  %s" % (v[0], v[1], v[2], v[3], k))
+        print("%5d %5d %5d %5d %5d  %s" % (v[0], v[1], v[2], v[3], v[4], k))
 
 
 if __name__ == "__main__":
