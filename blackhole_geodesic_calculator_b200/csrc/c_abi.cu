@@ -295,6 +295,7 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
     a.r_sphere = schw_radius(a.r_sphere);
     a.has_outer = std::isfinite(p->r_sphere) ? 1 : 0;
     a.rtol = p->rtol; a.atol = p->atol; a.max_step = p->max_step;
+    a.atol_over_rtol = a.atol / a.rtol; a.inv_rtol2 = 1.0 / (a.rtol * a.rtol);
     a.lambda_max = p->lambda_max > 0.0 ? p->lambda_max : 10.0 * p->r_sphere;
     // refill policy: explicit lane threshold, else the adaptive idle budget (lane-iterations per service)
     a.refill_threshold = p->refill_threshold;
@@ -739,14 +740,12 @@ int bhg_trace_camera_f64_host(const bhg_camera* cam, double* exit_pos, double* e
     if (n == 0) return 0;
     std::lock_guard<std::mutex> lk(c->host_mu);
     const size_t vec = (size_t)n * 3 * sizeof(double);
-    if ((rc = ensure_stage(c, 4 * vec + (size_t)n * 3 * sizeof(int32_t) + 1024))) return rc;
+    if ((rc = ensure_stage(c, 2 * vec + (size_t)n * 3 * sizeof(int32_t) + 1024))) return rc;
     DrainStreamsOnExit drain_streams_on_exit{c};
     char* base = (char*)c->stage;
-    double* d_pin = (double*)base;
-    double* d_din = (double*)(base + vec);
-    double* d_pout = (double*)(base + 2 * vec);
-    double* d_dout = (double*)(base + 3 * vec);
-    int32_t* d_status = (int32_t*)(base + 4 * vec);
+    double* d_pout = (double*)(base);
+    double* d_dout = (double*)(base + vec);
+    int32_t* d_status = (int32_t*)(base + 2 * vec);
     int32_t* d_cnt = d_status + n;
     // chunks are whole 8-row bands so that every chunk keeps the tile scheduling
     const long long chunk = pick_chunk(n, 8LL * cam->width);
@@ -800,14 +799,12 @@ int bhg_trace_camera_sky_host(const bhg_camera* cam, float* uv, int32_t* status,
     if (n == 0) return 0;
     std::lock_guard<std::mutex> lk(c->host_mu);
     const size_t vec = (size_t)n * 3 * sizeof(double);
-    if ((rc = ensure_stage(c, 3 * vec + (size_t)n * (8 + 4) + 1024))) return rc;
+    if ((rc = ensure_stage(c, vec + (size_t)n * (8 + 4) + 1024))) return rc;
     DrainStreamsOnExit drain_streams_on_exit{c};
     char* base = (char*)c->stage;
-    double* d_pin = (double*)base;
-    double* d_din = (double*)(base + vec);
-    double* d_dout = (double*)(base + 2 * vec);
-    float* d_uv = (float*)(base + 3 * vec);
-    int32_t* d_status = (int32_t*)(base + 3 * vec + (size_t)n * 8);
+    double* d_dout = (double*)(base);
+    float* d_uv = (float*)(base + vec);
+    int32_t* d_status = (int32_t*)(base + vec + (size_t)n * 8);
     const long long chunk = pick_chunk(n, 8LL * cam->width);
     int si = 0;
     for (long long b = 0; b < n; b += chunk, si = (si + 1) % 3) {

@@ -148,6 +148,7 @@ __device__ __forceinline__ double fifth_root(double a) {
 // [-pi/4, pi/4].  Branch-free.  The reduction is exact for |n| < 2^20 and stays within the argument's own
 // ulp up to |th| ~ 1e9; beyond that (a state that has already blown up) the result is NaN, which the step
 // controller treats like any other non-finite error norm.
+template <bool GUARD = true>
 __device__ __forceinline__ void sincos_tab(double th, double* s, double* c) {
     // n = rint(th * 2/pi) by the 1.5 * 2^52 trick: one FMA + one add, no FP64<->int conversion instructions
     const double big = 6755399441055744.0;
@@ -157,8 +158,12 @@ __device__ __forceinline__ void sincos_tab(double th, double* s, double* c) {
     double r = fma(-dn, TAB(T_PIO2_1), th);
     r = fma(-dn, TAB(T_PIO2_1T), r);
     // |th| >= 1e9 (0x41CDCD65 in the high word), inf or NaN -> NaN; integer compare keeps it off the FP64 pipe
-    const bool ok = (unsigned)(__double2hiint(th) & 0x7fffffff) < 0x41CDCD65u;
-    r = ok ? r : __longlong_as_double(0x7ff8000000000000LL);
+    // (GUARD = false: the RK45 attempt tests theta_new once per attempt instead - angle_in_range() - which spares the
+    // hot loop four ALU instructions per evaluation)
+    if (GUARD) {
+        const bool ok = (unsigned)(__double2hiint(th) & 0x7fffffff) < 0x41CDCD65u;
+        r = ok ? r : __longlong_as_double(0x7ff8000000000000LL);
+    }
     const double z = r * r;
     double ps = fma(z, TAB(T_S6), TAB(T_S5));
     double pc = fma(z, TAB(T_C6), TAB(T_C5));
@@ -179,6 +184,11 @@ __device__ __forceinline__ void sincos_tab(double th, double* s, double* c) {
     *c = __longlong_as_double(__double_as_longlong(b) ^ ((long long)((n + 1) & 2) << 62));
 }
 
+// |th| < 1e9: the range in which sincos_tab's reduction is valid (integer compare on the high word; false for NaN)
+__device__ __forceinline__ bool angle_in_range(double th) {
+    return (unsigned)(__double2hiint(th) & 0x7fffffff) < 0x41CDCD65u;
+}
+
 // ---------------------------------------------------------------------------------------------
 // right-hand sides: momentum derivatives only (positions' derivatives are the momenta themselves).
 //   NK = 4 (parity): k = (k_t, k_r, k_th, k_ph), x = (t, r, th, ph)
@@ -195,7 +205,7 @@ struct Rhs<4> {
                                                 double (&f)[4]) {
         const double kt = k[0], kr = k[1], kth = k[2], kph = k[3], r = x[1], th = x[2];
         double s, c;
-        sincos_tab(th, &s, &c);
+        sincos_tab<false>(th, &s, &c);
         const double rm = r - rs;
         const double p = r * rm;
         // one reciprocal for everything (two independent ones measured no faster on B200: r1 profiles)
@@ -268,7 +278,7 @@ __device__ __forceinline__ double xnew_component(double xi, double ki, double K0
 template <int NK>
 __device__ __forceinline__ double rk45_attempt(const double (&k)[NK], const double (&x)[NK], double (&K)[7][NK],
                                                double (&kn)[NK], double (&xn)[NK], const double h, const double rs,
-                                               const double rtol, const double atol) {
+                                               const double atol_over_rtol, const double inv_rtol2) {
     const double h2 = h * h;
     double kt[NK], xt[NK], hk[NK];
 #pragma unroll
@@ -355,8 +365,10 @@ __device__ __forceinline__ double rk45_attempt(const double (&k)[NK], const doub
         g = fma(TAB(EA4), K[3][i], g);
         g = fma(TAB(EA5), K[4][i], g);
         ex[i] = fma(TAB(EA6), K[5][i], g);         // error / h^2 (position half)
-        sk[i] = fma(fabs(larger_mag(k[i], kn[i])), rtol, atol);
-        sx[i] = fma(fabs(larger_mag(x[i], xn[i])), rtol, atol);
+        // scale / rtol = max(|y|, |y_new|) + atol / rtol: an addition with one constant instead of an FMA with two
+        // (the common factor 1 / rtol^2 of the squared norm is applied once, below)
+        sk[i] = fabs(larger_mag(k[i], kn[i])) + atol_over_rtol;
+        sx[i] = fabs(larger_mag(x[i], xn[i])) + atol_over_rtol;
     }
     // one reciprocal per group of four scales (two momentum/position pairs); scales are >= atol so the
     // products neither overflow nor underflow.  sum (e_i/scale_i)^2 = h^2 (S_k + h^2 S_x): h is applied once.
@@ -380,7 +392,9 @@ __device__ __forceinline__ double rk45_attempt(const double (&k)[NK], const doub
         sumk = fma(q0, q0, sumk);
         sumx = fma(q1, q1, sumx);
     }
-    const double esum = h2 * fma(h2, sumx, sumk);
+    double esum = (h2 * inv_rtol2) * fma(h2, sumx, sumk);
+    // a stage angle outside sincos_tab's range made this attempt meaningless: NaN rejects it (RHS evaluations are unguarded)
+    if (NK == 4 && !angle_in_range(xn[NK == 4 ? 2 : 0])) esum = __longlong_as_double(0x7ff8000000000000LL);
     return esum;
 }
 

@@ -30,6 +30,7 @@ struct TraceArgs {
     unsigned long long* queue_head;
     long long n;
     double rs, r_hor, r_sphere, rtol, atol, max_step, lambda_max;
+    double atol_over_rtol, inv_rtol2;  // the attempt's error norm works with scale / rtol (geodesic_core.cuh)
     int has_outer;
     int refill_threshold;  // > 0: service when this many lanes are idle
     int idle_budget;       // used when refill_threshold == 0: service when the idle lane-iterations accumulated
@@ -647,7 +648,7 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
                 const double h = t_new - t;  // >= 0: integration runs forward in lambda
                 h_abs = h;
                 n_attempt++;
-                const double esum = rk45_attempt<NK>(k, x, K, kn, xn, h, a.rs, a.rtol, a.atol);
+                const double esum = rk45_attempt<NK>(k, x, K, kn, xn, h, a.rs, a.atol_over_rtol, a.inv_rtol2);
                 // esum = 2 NK (RMS error norm)^2: accepted iff error norm < 1 (rk.py:148)
                 if (lt_nn(esum, 2.0 * NK)) {
                     n_accept++;
