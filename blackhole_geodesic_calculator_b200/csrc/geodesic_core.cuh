@@ -184,6 +184,28 @@ __device__ __forceinline__ void sincos_tab(double th, double* s, double* c) {
     *c = __longlong_as_double(__double_as_longlong(b) ^ ((long long)((n + 1) & 2) << 62));
 }
 
+// sin and cos for the RK45 attempt: th = n pi/64 + r with |r| <= pi/128; (sin, cos)(n pi/64) come from a 128-entry
+// table in shared memory, sin r and cos r - 1 from three-term series, and one rotation combines them.  16 FP64
+// instructions and 3 ALU ones instead of 20 and 10 for sincos_tab (whose quadrant swap / sign logic costs a cycle per
+// two-operand select, profiles/r2e_regread2.txt) and 8 polynomial constants instead of 12.  Error < 2 ulp.  No range
+// guard: see angle_in_range().
+__device__ __forceinline__ void sincos_lut(const double2* __restrict__ lut, double th, double* s, double* c) {
+    const double big = 6755399441055744.0;
+    const double tn = fma(th, TAB(T_L_64_OVER_PI), big);
+    const int n = __double2loint(tn);
+    const double dn = tn - big;
+    double r = fma(-dn, TAB(T_L_P1), th);
+    r = fma(-dn, TAB(T_L_P1T), r);
+    const double2 sc = lut[n & 127];
+    const double z = r * r;
+    const double ps = fma(z, fma(z, TAB(T_LS3), TAB(T_LS2)), TAB(T_LS1));
+    const double pc = fma(z, fma(z, TAB(T_LC3), TAB(T_LC2)), -0.5);
+    const double sr = fma(r, z * ps, r);  // sin r
+    const double cm = z * pc;             // cos r - 1
+    *s = fma(sc.y, sr, fma(sc.x, cm, sc.x));
+    *c = fma(-sc.x, sr, fma(sc.y, cm, sc.y));
+}
+
 // |th| < 1e9: the range in which sincos_tab's reduction is valid (integer compare on the high word; false for NaN)
 __device__ __forceinline__ bool angle_in_range(double th) {
     return (unsigned)(__double2hiint(th) & 0x7fffffff) < 0x41CDCD65u;
@@ -202,10 +224,11 @@ struct Rhs<4> {
     // which position components the RHS reads (r and theta): only those get stage values
     __device__ __forceinline__ static constexpr bool needs_x(int i) { return i == 1 || i == 2; }
     __device__ __forceinline__ static void eval(const double (&k)[4], const double (&x)[4], double rs,
-                                                double (&f)[4]) {
+                                                double (&f)[4], const double2* __restrict__ lut = nullptr) {
         const double kt = k[0], kr = k[1], kth = k[2], kph = k[3], r = x[1], th = x[2];
         double s, c;
-        sincos_tab<false>(th, &s, &c);
+        if (lut) sincos_lut(lut, th, &s, &c);
+        else sincos_tab<false>(th, &s, &c);
         const double rm = r - rs;
         const double p = r * rm;
         // one reciprocal for everything (two independent ones measured no faster on B200: r1 profiles)
@@ -233,7 +256,7 @@ template <>
 struct Rhs<3> {
     __device__ __forceinline__ static constexpr bool needs_x(int i) { return i == 1; }
     __device__ __forceinline__ static void eval(const double (&k)[3], const double (&x)[3], double rs,
-                                                double (&f)[3]) {
+                                                double (&f)[3], const double2* __restrict__ = nullptr) {
         const double kt = k[0], kr = k[1], kph = k[2], r = x[1];
         const double rm = r - rs;
         const double i_rrm = fast_rcp(r * rm);
@@ -278,7 +301,8 @@ __device__ __forceinline__ double xnew_component(double xi, double ki, double K0
 template <int NK>
 __device__ __forceinline__ double rk45_attempt(const double (&k)[NK], const double (&x)[NK], double (&K)[7][NK],
                                                double (&kn)[NK], double (&xn)[NK], const double h, const double rs,
-                                               const double atol_over_rtol, const double inv_rtol2) {
+                                               const double atol_over_rtol, const double inv_rtol2,
+                                               const double2* __restrict__ lut = nullptr) {
     const double h2 = h * h;
     double kt[NK], xt[NK], hk[NK];
 #pragma unroll
@@ -294,7 +318,7 @@ __device__ __forceinline__ double rk45_attempt(const double (&k)[NK], const doub
             kt[i] = fma(ha, K[0][i], k[i]);
             if (Rhs<NK>::needs_x(i)) xt[i] = fma(TAB(C2), hk[i], x[i]);
         }
-        Rhs<NK>::eval(kt, xt, rs, K[1]);
+        Rhs<NK>::eval(kt, xt, rs, K[1], lut);
     }
     // ---- stage 3
     {
@@ -303,7 +327,7 @@ __device__ __forceinline__ double rk45_attempt(const double (&k)[NK], const doub
             kt[i] = fma(h, fma(TAB(A32), K[1][i], TAB(A31) * K[0][i]), k[i]);
             if (Rhs<NK>::needs_x(i)) xt[i] = fma(h2, TAB(AA31) * K[0][i], fma(TAB(C3), hk[i], x[i]));
         }
-        Rhs<NK>::eval(kt, xt, rs, K[2]);
+        Rhs<NK>::eval(kt, xt, rs, K[2], lut);
     }
     // ---- stage 4
     {
@@ -313,7 +337,7 @@ __device__ __forceinline__ double rk45_attempt(const double (&k)[NK], const doub
             if (Rhs<NK>::needs_x(i))
                 xt[i] = fma(h2, fma(TAB(AA42), K[1][i], TAB(AA41) * K[0][i]), fma(TAB(C4), hk[i], x[i]));
         }
-        Rhs<NK>::eval(kt, xt, rs, K[3]);
+        Rhs<NK>::eval(kt, xt, rs, K[3], lut);
     }
     // ---- stage 5
     {
@@ -325,7 +349,7 @@ __device__ __forceinline__ double rk45_attempt(const double (&k)[NK], const doub
                 xt[i] = fma(h2, fma(TAB(AA53), K[2][i], fma(TAB(AA52), K[1][i], TAB(AA51) * K[0][i])),
                             fma(TAB(C5), hk[i], x[i]));
         }
-        Rhs<NK>::eval(kt, xt, rs, K[4]);
+        Rhs<NK>::eval(kt, xt, rs, K[4], lut);
     }
     // ---- stage 6 (c6 = 1)
     {
@@ -340,7 +364,7 @@ __device__ __forceinline__ double rk45_attempt(const double (&k)[NK], const doub
                             fma(TAB(AA64), K[3][i], fma(TAB(AA63), K[2][i], fma(TAB(AA62), K[1][i], TAB(AA61) * K[0][i]))),
                             x[i] + hk[i]);
         }
-        Rhs<NK>::eval(kt, xt, rs, K[5]);
+        Rhs<NK>::eval(kt, xt, rs, K[5], lut);
     }
     // ---- new state and FSAL stage
 #pragma unroll
@@ -348,7 +372,7 @@ __device__ __forceinline__ double rk45_attempt(const double (&k)[NK], const doub
         kn[i] = knew_component<NK>(k[i], K[0][i], K[2][i], K[3][i], K[4][i], K[5][i], h);
         xn[i] = xnew_component<NK>(x[i], k[i], K[0][i], K[1][i], K[2][i], K[3][i], K[4][i], h, h2);
     }
-    Rhs<NK>::eval(kn, xn, rs, K[6]);
+    Rhs<NK>::eval(kn, xn, rs, K[6], lut);
     // ---- error estimate, scaled (rk.py:143-146, common.py:63-65)
     double ek[NK], ex[NK], sk[NK], sx[NK];
 #pragma unroll

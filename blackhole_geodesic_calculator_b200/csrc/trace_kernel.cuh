@@ -475,6 +475,14 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
 
+    // (sin, cos)(n pi / 64) for the attempt's sincos_lut (parity mode; the plane system has no angle in its RHS)
+    __shared__ double2 s_sincos[NK == 4 ? 128 : 1];
+    if (NK == 4) {
+        for (int i = threadIdx.x; i < 128; i += blockDim.x) s_sincos[i] = make_double2(c_sincos_lut[i][0], c_sincos_lut[i][1]);
+        __syncthreads();
+    }
+    const double2* lut = (NK == 4) ? s_sincos : nullptr;
+
     double k[NK], x[NK], K[7][NK], kn[NK], xn[NK];
     double t = 0.0, h_abs = 0.0;
     long long idx = -1;
@@ -648,7 +656,7 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
                 const double h = t_new - t;  // >= 0: integration runs forward in lambda
                 h_abs = h;
                 n_attempt++;
-                const double esum = rk45_attempt<NK>(k, x, K, kn, xn, h, a.rs, a.atol_over_rtol, a.inv_rtol2);
+                const double esum = rk45_attempt<NK>(k, x, K, kn, xn, h, a.rs, a.atol_over_rtol, a.inv_rtol2, lut);
                 // esum = 2 NK (RMS error norm)^2: accepted iff error norm < 1 (rk.py:148)
                 if (lt_nn(esum, 2.0 * NK)) {
                     n_accept++;
