@@ -295,6 +295,7 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
     a.r_sphere = schw_radius(a.r_sphere);
     a.has_outer = std::isfinite(p->r_sphere) ? 1 : 0;
     a.rtol = p->rtol; a.atol = p->atol; a.max_step = p->max_step;
+    a.has_max_step = std::isfinite(a.max_step) ? 1 : 0;
     a.atol_over_rtol = a.atol / a.rtol; a.inv_rtol2 = 1.0 / (a.rtol * a.rtol);
     a.lambda_max = p->lambda_max > 0.0 ? p->lambda_max : 10.0 * p->r_sphere;
     // refill policy: explicit lane threshold, else the adaptive idle budget (lane-iterations per service)

@@ -106,6 +106,7 @@ __device__ __forceinline__ double pow_seed(double a, float e) {
     return (double)r;
 }
 
+template <bool CHECK = true>
 __device__ __forceinline__ double inv_tenth_root(double a) {
     const double x = pow_seed(a, -0.1f);
     const double x2 = x * x;
@@ -116,7 +117,9 @@ __device__ __forceinline__ double inv_tenth_root(double a) {
     double res = fma(x, p, x);
     // seed worse than 1e-5 (never with the MUFU seed) or NaN: cold library fallback.  Tested after the result is
     // formed so that the compare overlaps the polynomial instead of sitting on the serial path.
-    if (!abs_lt(d, 1e-4)) res = pow_cold(a, -0.1);
+    // CHECK = false: the step controller clamps its argument to [1e-11, 1e9] (NaN included), where the MUFU seed is
+    // always within 1e-6 - the fallback would be dead code that still costs ten ALU instructions and a call frame
+    if (CHECK && !abs_lt(d, 1e-4)) res = pow_cold(a, -0.1);
     return res;
 }
 
@@ -184,22 +187,23 @@ __device__ __forceinline__ void sincos_tab(double th, double* s, double* c) {
     *c = __longlong_as_double(__double_as_longlong(b) ^ ((long long)((n + 1) & 2) << 62));
 }
 
-// sin and cos for the RK45 attempt: th = n pi/64 + r with |r| <= pi/128; (sin, cos)(n pi/64) come from a 128-entry
-// table in shared memory, sin r and cos r - 1 from three-term series, and one rotation combines them.  16 FP64
+// sin and cos for the RK45 attempt: th = n pi/512 + r with |r| <= pi/1024; (sin, cos)(n pi/512) come from a 1024-entry
+// table in shared memory (16 KB), sin r and cos r - 1 from two-term series, and one rotation combines them.  14 FP64
 // instructions and 3 ALU ones instead of 20 and 10 for sincos_tab (whose quadrant swap / sign logic costs a cycle per
-// two-operand select, profiles/r2e_regread2.txt) and 8 polynomial constants instead of 12.  Error < 2 ulp.  No range
-// guard: see angle_in_range().
+// two-operand select, profiles/r2e_regread2.txt) and 6 constants instead of 15.  Error < 2 ulp.  No range guard: see
+// angle_in_range().
+constexpr int SINCOS_LUT_N = 1024;
 __device__ __forceinline__ void sincos_lut(const double2* __restrict__ lut, double th, double* s, double* c) {
     const double big = 6755399441055744.0;
-    const double tn = fma(th, TAB(T_L_64_OVER_PI), big);
+    const double tn = fma(th, TAB(T_L_N_OVER_PI), big);
     const int n = __double2loint(tn);
     const double dn = tn - big;
     double r = fma(-dn, TAB(T_L_P1), th);
     r = fma(-dn, TAB(T_L_P1T), r);
-    const double2 sc = lut[n & 127];
+    const double2 sc = lut[n & (SINCOS_LUT_N - 1)];
     const double z = r * r;
-    const double ps = fma(z, fma(z, TAB(T_LS3), TAB(T_LS2)), TAB(T_LS1));
-    const double pc = fma(z, fma(z, TAB(T_LC3), TAB(T_LC2)), -0.5);
+    const double ps = fma(z, TAB(T_LS2), TAB(T_LS1));
+    const double pc = fma(z, TAB(T_LC2), -0.5);
     const double sr = fma(r, z * ps, r);  // sin r
     const double cm = z * pc;             // cos r - 1
     *s = fma(sc.y, sr, fma(sc.x, cm, sc.x));
@@ -430,13 +434,13 @@ __device__ __forceinline__ double rk45_attempt(const double (&k)[NK], const doub
 template <int N2>
 __device__ __forceinline__ double step_factor_accept(double esum, double hi) {
     constexpr double c = (N2 == 8) ? 0.9 * 1.2311444133449163 : 0.9 * 1.1962311988513155;  // 0.9 * N2^(1/10)
-    return min_nn(c * inv_tenth_root(max_nn(esum, 1e-11)), hi);
+    return min_nn(c * inv_tenth_root<false>(min_nn(max_nn(esum, 1e-11), 1e9)), hi);
 }
 //   rejected: max(0.2, f); huge / inf / NaN error norms give 0.2 (min_nn drops the NaN; f(1e9) = 0.14)
 template <int N2>
 __device__ __forceinline__ double step_factor_reject(double esum) {
     constexpr double c = (N2 == 8) ? 0.9 * 1.2311444133449163 : 0.9 * 1.1962311988513155;
-    return max_nn(c * inv_tenth_root(min_nn(esum, 1e9)), 0.2);
+    return max_nn(c * inv_tenth_root<false>(max_nn(min_nn(esum, 1e9), 1e-11)), 0.2);
 }
 
 // 10 * |nextafter(t, +inf) - t|  for t >= 0 (scipy/_ivp/rk.py:119)

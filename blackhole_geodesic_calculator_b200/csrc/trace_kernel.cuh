@@ -32,6 +32,7 @@ struct TraceArgs {
     double rs, r_hor, r_sphere, rtol, atol, max_step, lambda_max;
     double atol_over_rtol, inv_rtol2;  // the attempt's error norm works with scale / rtol (geodesic_core.cuh)
     int has_outer;
+    int has_max_step;  // max_step is finite (the default is +inf: the clamp is then skipped by a uniform branch)
     int refill_threshold;  // > 0: service when this many lanes are idle
     int idle_budget;       // used when refill_threshold == 0: service when the idle lane-iterations accumulated
                            // since the last service reach this budget ("ski rental": idle until the waste equals
@@ -475,10 +476,11 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    // (sin, cos)(n pi / 64) for the attempt's sincos_lut (parity mode; the plane system has no angle in its RHS)
-    __shared__ double2 s_sincos[NK == 4 ? 128 : 1];
+    // (sin, cos)(n pi / 512) for the attempt's sincos_lut (parity mode; the plane system has no angle in its RHS)
+    __shared__ double2 s_sincos[NK == 4 ? SINCOS_LUT_N : 1];
     if (NK == 4) {
-        for (int i = threadIdx.x; i < 128; i += blockDim.x) s_sincos[i] = make_double2(c_sincos_lut[i][0], c_sincos_lut[i][1]);
+        const double2* g = reinterpret_cast<const double2*>(&g_sincos_lut[0][0]);
+        for (int i = threadIdx.x; i < SINCOS_LUT_N; i += blockDim.x) s_sincos[i] = __ldg(g + i);
         __syncthreads();
     }
     const double2* lut = (NK == 4) ? s_sincos : nullptr;
@@ -643,7 +645,7 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
             // ---------------- one RK45 attempt (rk.py:111-176) ----------------
             // min_step = 10 ulp(t) <= 2.3e-15 t: the exact value is only formed when h_abs is that small
             bool too_small = false;
-            if (!rejected && lt_nn(a.max_step, h_abs)) h_abs = a.max_step;
+            if (a.has_max_step && !rejected && lt_nn(a.max_step, h_abs)) h_abs = a.max_step;
             if (lt_nn(h_abs, t * 2.3e-15)) {
                 const double min_step = min_step_at(t);
                 if (!rejected && lt_nn(h_abs, min_step)) h_abs = min_step;

@@ -93,21 +93,21 @@ extra = [
     ("C1", 4.16666666666666019037e-02), ("C2", -1.38888888888741095749e-03), ("C3", 2.48015872894767294178e-05),
     ("C4", -2.75573143513906633035e-07), ("C5", 2.08757232129817482790e-09), ("C6", -1.13596475577881948265e-11),
 ]
-# sincos for the hot loop: angle = n pi/64 + r, |r| <= pi/128; (sin, cos)(n pi/64) from a 128-entry table (correctly
-# rounded, mpmath), sin r and cos r - 1 from three-term series (truncation 3.6e-19 / 3.3e-18), then one rotation
+# sincos for the hot loop: angle = n pi/512 + r, |r| <= pi/1024; (sin, cos)(n pi/512) from a 1024-entry table (correctly
+# rounded, mpmath), sin r and cos r - 1 from two-term series (truncation r^7/5040 -> 1.7e-19 relative, r^6/720 -> 1.2e-18),
+# then one rotation
 import mpmath
 mpmath.mp.prec = 200
-_p64 = mpmath.pi / 64
-_l_p1 = float.fromhex("0x1.921fb54400000p+0") / 32.0   # 33 significant bits: n * L_P1 is exact in the FMA
+_p64 = mpmath.pi / 512
+_l_p1 = float.fromhex("0x1.921fb54400000p+0") / 256.0   # 33 significant bits: n * L_P1 is exact in the FMA
 extra += [
-    ("L_64_OVER_PI", float(64 / mpmath.pi)), ("L_P1", _l_p1), ("L_P1T", float(_p64 - mpmath.mpf(_l_p1))),
-    ("LS1", float(-mpmath.mpf(1) / 6)), ("LS2", float(mpmath.mpf(1) / 120)), ("LS3", float(-mpmath.mpf(1) / 5040)),
-    ("LC2", float(mpmath.mpf(1) / 24)), ("LC3", float(-mpmath.mpf(1) / 720)),
+    ("L_N_OVER_PI", float(512 / mpmath.pi)), ("L_P1", _l_p1), ("L_P1T", float(_p64 - mpmath.mpf(_l_p1))),
+    ("LS1", float(-mpmath.mpf(1) / 6)), ("LS2", float(mpmath.mpf(1) / 120)), ("LC2", float(mpmath.mpf(1) / 24)),
 ]
-lut = [(float(mpmath.sin(n * _p64)), float(mpmath.cos(n * _p64))) for n in range(128)]
-for n in (0, 64):
+lut = [(float(mpmath.sin(n * _p64)), float(mpmath.cos(n * _p64))) for n in range(1024)]
+for n in (0, 512):
     lut[n] = (0.0, lut[n][1])
-for n in (32, 96):
+for n in (256, 768):
     lut[n] = (lut[n][0], 0.0)
 out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                    "blackhole_geodesic_calculator_b200", "csrc", "rk45_tables.cuh")
@@ -129,8 +129,8 @@ with open(out, "w") as f:
     for n, v in extra:
         f.write(f"    {v!r},  // {n}\n")
     f.write("};\n")
-    f.write("// (sin, cos)(n pi / 64), n = 0 .. 127, correctly rounded; copied to shared memory by the trace kernel\n")
-    f.write("__constant__ double c_sincos_lut[128][2] = {\n")
+    f.write("// (sin, cos)(n pi / 512), n = 0 .. 1023, correctly rounded; copied to shared memory by the trace kernel\n")
+    f.write("__device__ const double g_sincos_lut[1024][2] = {\n")
     for sv, cv in lut:
         f.write(f"    {{{sv!r}, {cv!r}}},\n")
     f.write("};\n}  // namespace bhg\n")
