@@ -245,9 +245,23 @@ bool prep_enabled() {
 }
 
 template <int NK, int IN, bool DISK, bool POLY>
-void launch_trace_variant(bool prep, int blocks, cudaStream_t stream, const bhg::TraceArgs& a) {
+void launch_trace_variant(bool prep, bool staged, int blocks, cudaStream_t stream, const bhg::TraceArgs& a) {
+    if constexpr (IN == bhg::IN_AOS && !DISK && !POLY) {
+        if (prep && staged) {  // exit states go to another GPU's memory: coalesce them through the staging tiles
+            bhg::trace_kernel<NK, IN, false, false, true, true><<<blocks, BHG_BLOCK, 0, stream>>>(a);
+            return;
+        }
+    }
     if (prep) bhg::trace_kernel<NK, IN, DISK, POLY, true><<<blocks, BHG_BLOCK, 0, stream>>>(a);
     else bhg::trace_kernel<NK, IN, DISK, POLY, false><<<blocks, BHG_BLOCK, 0, stream>>>(a);
+}
+
+// true when `p` is device memory of ANOTHER GPU (a bhg_ipc_open / peer mapping)
+bool is_remote(const void* p, int device) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeDevice && at.device != device;
 }
 
 template <int NK>
@@ -353,19 +367,20 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
         if (v > 0 && v < c.blocks_per_sm[mode][in_kind]) max_blocks = (long long)c.sm_count * v;
     }
     int blocks = (int)(want_blocks < max_blocks ? want_blocks : max_blocks);
+    const bool staged = is_remote(out_dir, (int)(&c - g_ctx));
     if (poly) {
-        if (disk) launch_trace_variant<4, bhg::IN_AOS, true, true>(prep, blocks, stream, a);
-        else launch_trace_variant<4, bhg::IN_AOS, false, true>(prep, blocks, stream, a);
+        if (disk) launch_trace_variant<4, bhg::IN_AOS, true, true>(prep, staged, blocks, stream, a);
+        else launch_trace_variant<4, bhg::IN_AOS, false, true>(prep, staged, blocks, stream, a);
     } else if (disk) {
-        launch_trace_variant<4, bhg::IN_AOS, true, false>(prep, blocks, stream, a);
+        launch_trace_variant<4, bhg::IN_AOS, true, false>(prep, staged, blocks, stream, a);
     } else if (mode == BHG_MODE_PARITY) {
-        if (in_kind == bhg::IN_AOS) launch_trace_variant<4, bhg::IN_AOS, false, false>(prep, blocks, stream, a);
-        else if (in_kind == bhg::IN_AOS_F32) launch_trace_variant<4, bhg::IN_AOS_F32, false, false>(prep, blocks, stream, a);
-        else launch_trace_variant<4, bhg::IN_SOA, false, false>(prep, blocks, stream, a);
+        if (in_kind == bhg::IN_AOS) launch_trace_variant<4, bhg::IN_AOS, false, false>(prep, staged, blocks, stream, a);
+        else if (in_kind == bhg::IN_AOS_F32) launch_trace_variant<4, bhg::IN_AOS_F32, false, false>(prep, staged, blocks, stream, a);
+        else launch_trace_variant<4, bhg::IN_SOA, false, false>(prep, staged, blocks, stream, a);
     } else {
-        if (in_kind == bhg::IN_AOS) launch_trace_variant<3, bhg::IN_AOS, false, false>(prep, blocks, stream, a);
-        else if (in_kind == bhg::IN_AOS_F32) launch_trace_variant<3, bhg::IN_AOS_F32, false, false>(prep, blocks, stream, a);
-        else launch_trace_variant<3, bhg::IN_SOA, false, false>(prep, blocks, stream, a);
+        if (in_kind == bhg::IN_AOS) launch_trace_variant<3, bhg::IN_AOS, false, false>(prep, staged, blocks, stream, a);
+        else if (in_kind == bhg::IN_AOS_F32) launch_trace_variant<3, bhg::IN_AOS_F32, false, false>(prep, staged, blocks, stream, a);
+        else launch_trace_variant<3, bhg::IN_SOA, false, false>(prep, staged, blocks, stream, a);
     }
     g_launches.fetch_add(1);
     BHG_CUDA(cudaGetLastError());
@@ -890,6 +905,33 @@ int bhg_ipc_close(void* ptr, int32_t device) {
     BHG_CUDA(cudaSetDevice(device));
     BHG_CUDA(cudaIpcCloseMemHandle(ptr));
     return 0;
+}
+
+namespace {
+// driver entry points without a link-time dependency on libcuda (the library must load on a machine without a driver)
+typedef int (*StreamMemOp32)(void* /*CUstream*/, unsigned long long /*CUdeviceptr*/, unsigned int, unsigned int);
+int stream_memop(const char* name, void* addr, int32_t value, unsigned flags, int32_t device, void* stream) {
+    if (!addr || ((uintptr_t)addr & 3)) return fail(BHG_ERR_INVALID_ARGUMENT, "%s: NULL or misaligned address", name);
+    DeviceRestore restore_device_on_exit;
+    DeviceCtx* c;
+    int rc = ensure_device(device, &c);
+    if (rc) return rc;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    BHG_CUDA(cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) return fail(BHG_ERR_CUDA, "%s is not available in this driver", name);
+    const int r = ((StreamMemOp32)fn)(stream, (unsigned long long)(uintptr_t)addr, (unsigned int)value, flags);
+    if (r != 0) return fail(BHG_ERR_CUDA, "%s failed with CUresult %d", name, r);
+    return 0;
+}
+}  // namespace
+
+int bhg_stream_write32(void* addr, int32_t value, int32_t device, void* stream) {
+    return stream_memop("cuStreamWriteValue32", addr, value, 0u /* CU_STREAM_WRITE_VALUE_DEFAULT */, device, stream);
+}
+
+int bhg_stream_wait_geq32(void* addr, int32_t value, int32_t device, void* stream) {
+    return stream_memop("cuStreamWaitValue32", addr, value, 0u /* CU_STREAM_WAIT_VALUE_GEQ */, device, stream);
 }
 
 int bhg_copy_rows(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t row_bytes, int64_t rows,

@@ -468,7 +468,8 @@ __global__ void __launch_bounds__(256) prepare_kernel(const TraceArgs a, const C
 #define BHG_BLOCK 512
 #endif
 
-template <int NK, int IN, bool DISK = false, bool POLY = false, bool PREP = false>
+// STAGE: the launcher selects it when the output buffers live in another GPU's memory (it costs 0.6 % on local ones)
+template <int NK, int IN, bool DISK = false, bool POLY = false, bool PREP = false, bool STAGE = false>
 __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const TraceArgs a) {
     static_assert(!(DISK || POLY) || NK == 4, "disk event and polyline are defined for the spherical (parity) state");
     constexpr int IR = 1;  // index of r in x
@@ -484,6 +485,13 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
         __syncthreads();
     }
     const double2* lut = (NK == 4) ? s_sincos : nullptr;
+    // Exit states of the float64 AoS layout leave through a per-warp staging tile: the lanes that finish in one service
+    // put their 6 doubles there and the whole warp writes them out element-wise, so rays that are neighbours in memory
+    // (4 per tile row, 32 without the tile mapping) become runs of full 32-byte sectors instead of 8-byte pieces at a
+    // 24-byte stride.  Local HBM does not care; a frame owner's memory behind NVLink does (distributed.py "stores").
+    constexpr bool STAGED = STAGE && (IN == IN_AOS);
+    __shared__ double s_stage[STAGED ? BHG_BLOCK / 32 : 1][STAGED ? 6 : 1][32];
+    double (*stage)[32] = s_stage[STAGED ? (threadIdx.x >> 5) : 0];
 
     double k[NK], x[NK], K[7][NK], kn[NK], xn[NK];
     double t = 0.0, h_abs = 0.0;
@@ -523,6 +531,8 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
         if (service) {
             idle_acc = 0;
             // ---------------- finish pending lanes ----------------
+            const unsigned fin = STAGED ? __ballot_sync(FULL, state != LANE_RUNNING && state != LANE_EMPTY) : 0u;
+            const long long fin_idx = idx;
             if (state != LANE_RUNNING && state != LANE_EMPTY) {
                 int final_status = state;
                 if (state < LANE_RUNNING) {
@@ -580,12 +590,42 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
                     exit_state<NK>(k, x, x0, k0, xo, ko);
                     if (a.coords) schw_to_iso(a.rs, xo, ko);
                 }
-                store_ray<IN>(a, idx, xo, ko, final_status, n_attempt, n_accept);
+                if constexpr (STAGED) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        stage[c][lane] = xo[c];
+                        stage[3 + c][lane] = ko[c];
+                    }
+                    a.status[idx] = final_status;
+                    if (a.counters) {
+                        a.counters[idx] = n_attempt;
+                        a.counters[a.n + idx] = n_accept;
+                    }
+                } else {
+                    store_ray<IN>(a, idx, xo, ko, final_status, n_attempt, n_accept);
+                }
                 if constexpr (POLY) a.poly_count[idx] = pj;
                 if constexpr (DISK) {
                     if (!disk_hit) a.disk_xy[2 * idx] = a.disk_xy[2 * idx + 1] = __longlong_as_double(0x7ff8000000000000LL);
                 }
                 state = LANE_EMPTY;
+            }
+            if constexpr (STAGED) {
+                if (fin) {
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 3; j++) {
+                        const int e = 32 * j + lane;        // element e of the tile: ray slot e / 3, component e % 3
+                        const int sl = e / 3;
+                        const int c = e - 3 * sl;
+                        const long long i = __shfl_sync(FULL, fin_idx, sl);
+                        if ((fin >> sl) & 1u) {
+                            if (a.out) a.out[3 * i + c] = stage[c][sl];
+                            a.out_dir[3 * i + c] = stage[3 + c][sl];
+                        }
+                    }
+                    __syncwarp();
+                }
             }
             // ---------------- refill idle lanes ----------------
             if (!exhausted) {

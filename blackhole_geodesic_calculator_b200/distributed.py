@@ -158,12 +158,19 @@ class PeerFrame:
         align = lambda b: (b + 255) & ~255
         self._off_dir = align(self.n * 24)
         self._off_status = self._off_dir + align(self.n * 24)
-        total = self._off_status + self.n * 4
+        # flags (int32, zero at creation): [r] = last epoch whose shard of rank r has arrived, [world] = last epoch
+        # for which the owner has released the buffers to the writers
+        self._off_flags = self._off_status + align(self.n * 4)
+        total = self._off_flags + align((self.world + 1) * 4)
+        self._epoch = 0
         base = ctypes.c_void_p()
         handle = None
         self.is_owner = self.rank == self.owner
         if self.is_owner:
             self._check(self._lib.bhg_device_alloc(total, self.device, ctypes.byref(base)))
+            torch.as_tensor(_DevicePointerView(base.value + self._off_flags, (self.world + 1,), "<i4"),
+                            device=torch.device("cuda", self.device)).zero_()
+            torch.cuda.synchronize(self.device)
             if self.world > 1:
                 buf = ctypes.create_string_buffer(64)
                 self._check(self._lib.bhg_ipc_export(base, self.device, buf))
@@ -224,6 +231,31 @@ class PeerFrame:
         if self.world > 1:
             dist.all_reduce(self._token, group=self.group)
 
+    # ---- flag protocol (stream memory operations on the owner's memory; no collective, no SM) ----
+    def _flag_ptr(self, i):
+        return self._base + self._off_flags + 4 * i
+
+    def begin_epoch(self, stream):
+        """Start a new frame: the owner releases the buffers (ordered after whatever its stream did with the previous
+        frame), the other ranks' streams wait for that release before they may write."""
+        self._epoch += 1
+        if self.world == 1:
+            return
+        if self.is_owner:
+            self._check(self._lib.bhg_stream_write32(self._flag_ptr(self.world), self._epoch, self.device, stream))
+        else:
+            self._check(self._lib.bhg_stream_wait_geq32(self._flag_ptr(self.world), self._epoch, self.device, stream))
+
+    def end_epoch(self, stream):
+        """Finish the frame: every rank posts its arrival after its last write; the owner's stream waits for all."""
+        if self.world == 1:
+            return
+        self._check(self._lib.bhg_stream_write32(self._flag_ptr(self.rank), self._epoch, self.device, stream))
+        if self.is_owner:
+            for r in range(self.world):
+                if r != self.rank:
+                    self._check(self._lib.bhg_stream_wait_geq32(self._flag_ptr(r), self._epoch, self.device, stream))
+
     def close(self):
         import torch
 
@@ -254,7 +286,7 @@ def band_plan(n: int, rank: int, world: int, image_width: int = 0, band: int = 8
 
 
 def trace_sharded_peer(entry_pos, entry_dir, frame: PeerFrame, *, image_width=0, fence_before=True, route="auto",
-                       chunks=2, **trace_kw):
+                       chunks=2, sync="flags", **trace_kw):
     """Trace one frame across all ranks and deliver the exit states into `frame` (the owner's HBM) without a gather.
 
     entry_pos / entry_dir: the frame's full [n,3] float64 CUDA tensors, present on every rank (each rank generates
@@ -267,37 +299,55 @@ def trace_sharded_peer(entry_pos, entry_dir, frame: PeerFrame, *, image_width=0,
                second pass at all, but 24-byte remote stores: best at 2 GPUs, ingress-bound at 8
                (profiles/r1q_strong_frame_n8.json);
       "auto"   "stores" up to 2 ranks, "copy" beyond.
-    A closing 1-element all-reduce orders the owner's stream after every rank's work; `fence_before` adds the same
-    fence ahead so the owner's consumer of the previous frame has finished before anyone overwrites the buffers.
+    sync="flags" (default): arrival flags in the owner's memory, written and awaited with stream memory operations
+    (PeerFrame.begin_epoch / end_epoch) - nothing that needs an SM or a collective; sync="nccl": a closing 1-element
+    all-reduce orders the owner's stream after every rank's work.  `fence_before` orders every rank's writes after the
+    owner's release of the buffers (its consumer of the previous frame has finished).
     Returns the owner's (exit_pos, exit_dir, status) views, None elsewhere.  Asynchronous on the current stream."""
     import torch
     from . import api
 
     if entry_pos.shape[0] != frame.n:
         raise ValueError("trace_sharded_peer: frame was built for a different ray count")
-    if route == "auto":
-        route = "stores" if frame.world <= 2 else "copy"
-    if route not in ("copy", "stores"):
-        raise ValueError("route must be 'auto', 'copy' or 'stores'")
     dev = entry_pos.device
     cur = torch.cuda.current_stream(dev)
+    if route == "auto":
+        route = "stores"
+    if sync not in ("flags", "nccl"):
+        raise ValueError("sync must be 'flags' or 'nccl'")
+
+    def open_frame():
+        if sync == "flags":
+            if fence_before:
+                frame.begin_epoch(cur.cuda_stream)
+            else:
+                frame._epoch += 1
+        elif fence_before:
+            frame.fence()
+
+    def close_frame():
+        if sync == "flags":
+            frame.end_epoch(cur.cuda_stream)
+        else:
+            frame.fence()
+
+    if route not in ("copy", "stores"):
+        raise ValueError("route must be 'auto', 'copy' or 'stores'")
     if route == "stores":
         order = frame.order(image_width)
         params = api.make_params(**trace_kw)
-        if fence_before:
-            frame.fence()
+        open_frame()
         if order.numel():
             api.trace_device(entry_pos.data_ptr(), entry_dir.data_ptr(), frame.pos_ptr, frame.dir_ptr,
                              frame.status_ptr, None, order.data_ptr(), order.numel(), api.LAYOUT_AOS, params,
                              device=dev.index, stream=cur.cuda_stream)
-        frame.fence()
+        close_frame()
         return frame.tensors()
 
     plan = frame.copy_plan(image_width)
     band, m, W, r = plan["band"], plan["m"], frame.world, frame.rank
     params = api.make_params(image_width=image_width if plan["tiles_ok"] else 0, **trace_kw)
-    if fence_before:
-        frame.fence()
+    open_frame()
     if m:
         side, lib = plan["side"], frame._lib
         nb_local = (m + band - 1) // band
@@ -335,7 +385,7 @@ def trace_sharded_peer(entry_pos, entry_dir, frame: PeerFrame, *, image_width=0,
                                                    src + (lo + full * band) * width, tail * width, tail * width, 1,
                                                    dev.index, side.cuda_stream))
         cur.wait_stream(side)
-    frame.fence()
+    close_frame()
     return frame.tensors()
 
 

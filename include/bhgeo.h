@@ -233,6 +233,14 @@ int bhg_ipc_close(void* ptr, int32_t device);
 int bhg_copy_rows(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t row_bytes, int64_t rows,
                   int32_t device, void* stream);
 
+/* Stream-ordered 32-bit flag in device memory (driver stream memory operations, executed by the GPU front end: they
+ * need no SM, so they progress while a persistent trace kernel owns every register file).  `addr` may be a
+ * bhg_ipc_open mapping: the ranks of a sharded frame post "my shard has arrived" into the frame owner's memory with
+ * bhg_stream_write32 after their trace kernel and the owner's stream waits for all of them with
+ * bhg_stream_wait_geq32 - no collective, no host synchronisation.  wait: (int32)*addr - value >= 0. */
+int bhg_stream_write32(void* addr, int32_t value, int32_t device, void* stream);
+int bhg_stream_wait_geq32(void* addr, int32_t value, int32_t device, void* stream);
+
 /* PCI bus id of `device` ("0000:1b:00.0"), so that a host process can place its pinned frame buffers on the NUMA
  * node the GPU hangs off (api.pinned_empty(..., device=)); buf needs >= 16 bytes. */
 int bhg_device_pci_bus_id(int32_t device, char* buf, int32_t len);

@@ -45,12 +45,12 @@ def reg_operands(txt, prev_reuse):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--lib", default=os.path.join(ROOT, "blackhole_geodesic_calculator_b200", "lib", "libbhgeo.so"))
-    ap.add_argument("--kernel", default="4,1,0,0,1")
+    ap.add_argument("--kernel", default="4,1,0,0,1,0")
     ap.add_argument("--top", type=int, default=60)
     ap.add_argument("--first-line", type=int, default=0, help="first line of the attempt in trace_kernel.cuh (auto)")
     a = ap.parse_args()
     t = [int(v) for v in a.kernel.split(",")]
-    name = "_ZN3bhg12trace_kernelILi%dELi%dELb%dELb%dELb%dEEEvNS_9TraceArgsE" % tuple(t)
+    name = "_ZN3bhg12trace_kernelILi%dELi%dELb%dELb%dELb%dELb%dEEEvNS_9TraceArgsE" % tuple(t)
     txt = disassemble(a.lib)
     start = txt.index(".text." + name + ":")
     end = txt.find("//--------------------- .text.", start)

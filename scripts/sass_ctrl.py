@@ -9,12 +9,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--lib", default=os.path.join(ROOT, "blackhole_geodesic_calculator_b200", "lib", "libbhgeo.so"))
-    ap.add_argument("--kernel", default="4,1,0,0,1")
+    ap.add_argument("--kernel", default="4,1,0,0,1,0")
     ap.add_argument("--start", default="0")
     ap.add_argument("--end", default="0xffffff")
     a = ap.parse_args()
     t = [int(v) for v in a.kernel.split(",")]
-    name = "trace_kernelILi%dELi%dELb%dELb%dELb%dEEE" % tuple(t)
+    name = "trace_kernelILi%dELi%dELb%dELb%dELb%dELb%dEEE" % tuple(t)
     txt = subprocess.run(["cuobjdump", "-sass", a.lib], capture_output=True, text=True, check=True).stdout
     part = [p for p in txt.split("Function : ")[1:] if name in p.splitlines()[0]][0]
     lines = part.splitlines()

@@ -29,7 +29,7 @@ def is_fp64(op):
 def kernel_sass(lib, tmpl):
     txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
     a = [int(v) for v in tmpl.split(",")]
-    name = "trace_kernelILi%dELi%dELb%dELb%dELb%dEEE" % tuple(a)
+    name = "trace_kernelILi%dELi%dELb%dELb%dELb%dELb%dEEE" % tuple(a)
     parts = txt.split("Function : ")
     for p in parts[1:]:
         if name in p.splitlines()[0]:
@@ -40,7 +40,7 @@ def kernel_sass(lib, tmpl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--lib", default=os.path.join(ROOT, "blackhole_geodesic_calculator_b200", "lib", "libbhgeo.so"))
-    ap.add_argument("--kernel", default="4,1,0,0,1")
+    ap.add_argument("--kernel", default="4,1,0,0,1,0")
     ap.add_argument("--dump", default=None)
     a = ap.parse_args()
     ins = []

@@ -173,9 +173,16 @@ def _nccl_worker(rank, world, port, q):
         frame = distributed.PeerFrame(tp.shape[0], owner=0)
         try:
             peer = []
-            for route, w, chunks in (("stores", 0, 1), ("stores", 64, 1), ("copy", 0, 1), ("copy", 64, 3)):
-                res = distributed.trace_sharded_peer(tp, td, frame, image_width=w, route=route, chunks=chunks)
+            # arrival flags by stream memory operations (default) and the NCCL fence, both routes, twice in a row so
+            # that the second frame has to wait for the owner's release of the buffers
+            for route, w, chunks, sync in (("stores", 0, 1, "flags"), ("stores", 64, 1, "flags"), ("copy", 0, 1, "flags"),
+                                           ("copy", 64, 3, "nccl"), ("stores", 64, 1, "nccl"), ("stores", 64, 1, "flags")):
+                if rank == 0:
+                    frame.tensors()[2].fill_(-7)
+                res = distributed.trace_sharded_peer(tp, td, frame, image_width=w, route=route, chunks=chunks, sync=sync)
+                torch.cuda.synchronize()
                 peer.append(None if res is None else [t.clone() for t in res])
+                dist.barrier()
             torch.cuda.synchronize()
             # ragged frame: the last band is partial and 3 pieces do not divide the bands
             m = 3 * 8192 + 77
@@ -195,7 +202,7 @@ def _nccl_worker(rank, world, port, q):
                 ok = ok and ok2 and all(torch.equal(a, b) for pr in peer for a, b in zip(pr, ref))
                 q.put("ok" if ok else "mismatch")
             else:
-                q.put("none" if out is None and peer == [None] * 4 else "unexpected")
+                q.put("none" if out is None and peer == [None] * 6 else "unexpected")
         finally:
             frame.close()
     finally:
