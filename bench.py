@@ -217,27 +217,41 @@ def strong_frame(args, dev, local, rank, world, n1_ms):
         iters = max(3, min(args.steps, 10))
         routes = {}
         equal = True
-        for route, sync in (("stores", "flags"), ("copy", "flags"), ("stores", "nccl")):
+        variants = [("courier", "flags", W, 1), ("stores", "flags", 0, 1), ("copy", "flags", W, 2), ("courier", "nccl", W, 1)]
+        for route, sync, width, chunks in variants:
             if rank == 0:
                 frame.tensors()[2].fill_(-7)
-            call = lambda: D.trace_sharded_peer(pos0, d0, frame, image_width=W, route=route, sync=sync, **kw)
+            call = lambda: D.trace_sharded_peer(pos0, d0, frame, image_width=width, route=route, sync=sync,
+                                                chunks=chunks, **kw)
             res = call()
             torch.cuda.synchronize(dev)
             dist.barrier()
             if rank == 0:
                 equal = equal and same(res, single)
             med, best = timed(call, iters)
-            routes[f"{route}/{sync}"] = {"ms_median": med, "ms_min": best}
+            routes[f"{route}/{sync}/w{width}/c{chunks}"] = {"ms_median": med, "ms_min": best}
+        # floor: the same shard integrated into LOCAL buffers (no delivery at all)
+        order = frame.order(0)
+        lp, ld = torch.empty_like(pos0), torch.empty_like(d0)
+        ls = torch.empty(n, dtype=torch.int32, device=dev)
+        prm = api.make_params(**kw)
+        local_call = lambda: api.trace_device(pos0.data_ptr(), d0.data_ptr(), lp.data_ptr(), ld.data_ptr(), ls.data_ptr(),
+                                              None, order.data_ptr(), order.numel(), api.LAYOUT_AOS, prm, local,
+                                              torch.cuda.current_stream(dev).cuda_stream)
+        local_call()
+        out["shard_compute_only_ms"] = timed(local_call, iters)[0]
         g_med, _ = timed(lambda: D.trace_sharded(pos0, d0, **kw), iters)
         best_route = min(routes, key=lambda r: routes[r]["ms_median"])
         t_ms = routes[best_route]["ms_median"]
         out.update({"route": best_route, "ms": t_ms, "value": n / (t_ms * 1e-3), "unit": "rays/s",
                     "efficiency_vs_n1": (n1_ms / (world * t_ms)) if n1_ms else None,
                     "ms_by_route": routes, "nccl_gather_route_ms": g_med, "peer_equals_single": equal if rank == 0 else None,
-                    "what": "one 1024x1024x5spp frame: rays dealt to the ranks in 32-ray groups, every rank's trace "
-                            "kernel stores its exit states into rank 0's HBM over NVLink (staged, coalesced stores); "
-                            "arrival flags by stream memory operations; timed from the call to the owner's stream "
-                            "having every shard (max over ranks)"})
+                    "what": "one 1024x1024x5spp frame: 8-row bands dealt cyclically to the ranks; routes: courier = one "
+                            "trace launch per rank whose finished bands a 2-SM courier kernel stores into rank 0's HBM "
+                            "over NVLink while the integration runs, stores = the trace kernel's own (staged) remote "
+                            "stores, copy = pieces + copy-engine deliveries; arrival flags by stream memory operations "
+                            "(or an NCCL fence); timed from the call to the owner's stream having every shard (max "
+                            "over ranks)"})
     finally:
         frame.close()
     return out

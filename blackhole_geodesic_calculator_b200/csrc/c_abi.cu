@@ -141,6 +141,7 @@ struct DeviceCtx {
     void* stage = nullptr;
     size_t stage_bytes = 0;
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t courier_stream = nullptr;   // bhg_trace_frame_shard_f64 (created on first use)
     // pinned bounce buffers for pageable user arrays (3 pipeline slots), grow-only
     void* bounce = nullptr;
     size_t bounce_bytes = 0;
@@ -236,6 +237,35 @@ int convert_camera(const bhg_camera* cam, double r_sphere, bhg::Camera* out) {
 }
 
 // The pre-pass (prepare_kernel) is the default; BHG_PREP=0 keeps the initialisation inside the trace kernel (A/B runs)
+// Cost binning of bundles that carry no image order (cost_key_kernel): on unless BHG_BIN=0; BHG_BIN=2 forces it even
+// when the caller gave the image_width hint (experiments)
+int bin_mode() {
+    static const int v = [] {
+        const char* e = getenv("BHG_BIN");
+        return e ? atoi(e) : 1;
+    }();
+    return v;
+}
+
+template <int IN>
+void launch_cost_passes(int sample_blocks, int blocks, cudaStream_t stream, const bhg::TraceArgs& a, unsigned char* keys,
+                        int* hist, int32_t* sorted, int force) {
+    bhg::cost_sample_kernel<IN><<<sample_blocks, 256, 0, stream>>>(a, hist);
+    bhg::cost_decide_kernel<<<1, 32, 0, stream>>>(hist, force);
+    bhg::cost_key_kernel<IN><<<blocks, 256, 0, stream>>>(a, keys, hist);
+    bhg::cost_offsets_kernel<<<1, 32, 0, stream>>>(hist);
+    bhg::cost_scatter_kernel<<<blocks, 256, 0, stream>>>(a.n, a.order, keys, hist, sorted);
+}
+
+// long rays first (trace_kernel.cuh TraceArgs::hot_list): on unless BHG_HOT=0
+bool hot_enabled() {
+    static const int v = [] {
+        const char* e = getenv("BHG_HOT");
+        return (e && atoi(e) == 0) ? 0 : 1;
+    }();
+    return v != 0;
+}
+
 bool prep_enabled() {
     static const int v = [] {
         const char* e = getenv("BHG_PREP");
@@ -273,12 +303,20 @@ void launch_prepare_variant(int in_kind, bool from_camera, int blocks, cudaStrea
     else bhg::prepare_kernel<NK, bhg::IN_SOA><<<blocks, 256, 0, stream>>>(a, cam, nullptr, nullptr);
 }
 
+// sharded frames (bhg_trace_frame_shard_f64): band progress counters for the courier and SMs left free for it
+struct ShardHook {
+    int* band_done;
+    long long band_rays;
+    int reserve_sms;
+    long long map_first, map_stride;   // input mapping (TraceArgs::map_*): bands of band_rays, stride 0 = compact input
+};
+
 // in_kind: bhg::IN_SOA / IN_AOS / IN_AOS_F32.  `cam` != NULL: the rays come from the camera description (in / in_dir
 // are ignored; outputs are AoS) - parity mode needs no ray buffer at all, plane mode keeps one for its exit frame.
 int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* out, double* out_dir, int32_t* status,
                  int32_t* counters, const int32_t* order, long long n, int in_kind, int image_width,
                  const bhg_params* p, cudaStream_t stream, const bhg_extras* ex = nullptr,
-                 const bhg::Camera* cam = nullptr) {
+                 const bhg::Camera* cam = nullptr, const ShardHook* hook = nullptr) {
     if (n == 0) return 0;
     const bool disk = ex && ex->disk_xy && ex->disk_r_out > 0.0;
     const bool poly = ex && ex->poly_n >= 2 && ex->poly_xyz && ex->poly_count;
@@ -293,6 +331,11 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
     bhg::TraceArgs a;
     memset(&a, 0, sizeof(a));
     a.in = in; a.in_dir = in_dir; a.out = out; a.out_dir = out_dir;
+    if (hook) {
+        a.band_done = hook->band_done;
+        a.band_rays = hook->band_rays;
+        if (hook->map_stride > 0) { a.map_band = hook->band_rays; a.map_first = hook->map_first; a.map_stride = hook->map_stride; }
+    }
     a.status = status; a.counters = counters; a.order = order;
     a.n = n;
     a.rs = 2.0 * p->M;
@@ -339,12 +382,51 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
     a.queue_head = c.queue_slots + slot;
     BHG_CUDA(cudaMemsetAsync(a.queue_head, 0, sizeof(unsigned long long), stream));
     const int mode = p->mode;
+    // ---- cost binning: a bundle without image order is served costliest class first (unless found coherent)
+    void* bin_scratch = nullptr;
+    const int bm = bin_mode();
+    if (!cam && n >= 4096 && n < (1LL << 31) && ((bm == 1 && a.tile_width == 0) || bm == 2)) {
+        const size_t keys_bytes = ((size_t)n + 255) & ~(size_t)255;
+        BHG_CUDA(cudaMallocAsync(&bin_scratch, keys_bytes + 512 + (size_t)n * sizeof(int32_t), stream));
+        unsigned char* keys = (unsigned char*)bin_scratch;
+        int* hist = (int*)(keys + keys_bytes);          // counts, cursors, sample statistics, keep flag (trace_kernel.cuh)
+        int32_t* sorted = (int32_t*)(keys + keys_bytes + 512);
+        BHG_CUDA(cudaMemsetAsync(hist, 0, 512, stream));
+        long long kb = (n + 255) / 256;
+        if (kb > c.sm_count * 8LL) kb = c.sm_count * 8LL;
+        long long sb = (n / (32 * bhg::COST_SAMPLE_STRIDE) + 7) / 8;
+        if (sb < 1) sb = 1;
+        if (sb > c.sm_count * 8LL) sb = c.sm_count * 8LL;
+        bhg::TraceArgs ka = a;
+        if (bm == 2) ka.tile_width = 0;
+        const int force = bm == 2 ? 1 : 0;
+        if (in_kind == bhg::IN_AOS) launch_cost_passes<bhg::IN_AOS>((int)sb, (int)kb, stream, ka, keys, hist, sorted, force);
+        else if (in_kind == bhg::IN_AOS_F32) launch_cost_passes<bhg::IN_AOS_F32>((int)sb, (int)kb, stream, ka, keys, hist, sorted, force);
+        else launch_cost_passes<bhg::IN_SOA>((int)sb, (int)kb, stream, ka, keys, hist, sorted, force);
+        g_launches.fetch_add(5);
+        BHG_CUDA(cudaGetLastError());
+        a.sorted = sorted;
+        a.sort_keep = hist + 2 * bhg::COST_BINS + 2;
+        if (bm == 2) a.tile_width = 0;
+    }
     // ---- pre-pass: prepared rays in queue order (stream-ordered scratch)
     const bool prep = prep_enabled() || cam != nullptr;
     double* cam_rays = nullptr;
     if (prep) {
         const int planes = (mode == BHG_MODE_PARITY) ? 6 : 4;
-        BHG_CUDA(cudaMallocAsync((void**)&a.prep, (size_t)n * planes * sizeof(double2), stream));
+        // prepared records + the long-ray list: [count 256 B][mask][list]
+        const size_t rec_bytes = (size_t)n * planes * sizeof(double2);
+        const size_t mask_bytes = ((((size_t)n + 31) / 32) * 4 + 255) & ~(size_t)255;
+        // the tail of a launch is a fixed ~0.05 ms: worth the list (+0.6 % pre-pass work) only below ~30 rays per lane
+        const bool hot = hot_enabled() && n <= (1LL << 21);
+        BHG_CUDA(cudaMallocAsync((void**)&a.prep, rec_bytes + (hot ? 256 + mask_bytes + (size_t)n * 4 : 0), stream));
+        if (hot) {
+            char* hb = (char*)a.prep + rec_bytes;
+            a.hot_count = (unsigned long long*)hb;
+            a.hot_mask = (unsigned int*)(hb + 256);
+            a.hot_list = (int32_t*)(hb + 256 + mask_bytes);
+            BHG_CUDA(cudaMemsetAsync(hb, 0, 256 + mask_bytes, stream));
+        }
         if (cam && mode == BHG_MODE_PLANE) {  // the orbital-plane frame is rebuilt from the flat entry state at the exit
             BHG_CUDA(cudaMallocAsync((void**)&cam_rays, (size_t)n * 48, stream));
             a.in = cam_rays;
@@ -366,6 +448,10 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
         int v = atoi(e);
         if (v > 0 && v < c.blocks_per_sm[mode][in_kind]) max_blocks = (long long)c.sm_count * v;
     }
+    if (hook) {
+        const long long keep = (long long)(c.sm_count - hook->reserve_sms) * c.blocks_per_sm[mode][in_kind];
+        if (keep >= 1 && keep < max_blocks) max_blocks = keep;
+    }
     int blocks = (int)(want_blocks < max_blocks ? want_blocks : max_blocks);
     const bool staged = is_remote(out_dir, (int)(&c - g_ctx));
     if (poly) {
@@ -384,6 +470,7 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
     }
     g_launches.fetch_add(1);
     BHG_CUDA(cudaGetLastError());
+    if (bin_scratch) cudaFreeAsync(bin_scratch, stream);
     if (a.prep) cudaFreeAsync(a.prep, stream);
     if (cam_rays) cudaFreeAsync(cam_rays, stream);
     return 0;
@@ -905,6 +992,71 @@ int bhg_ipc_close(void* ptr, int32_t device) {
     BHG_CUDA(cudaSetDevice(device));
     BHG_CUDA(cudaIpcCloseMemHandle(ptr));
     return 0;
+}
+
+int bhg_trace_frame_shard_f64(const double* entry_pos, const double* entry_dir, int32_t entry_is_frame, int64_t m,
+                              double* frame_pos, double* frame_dir, int32_t* frame_status, int64_t band_rays,
+                              int64_t first_band, int64_t band_stride, const bhg_params* params, int32_t device,
+                              void* stream) {
+    const double* shard_pos = entry_pos;
+    const double* shard_dir = entry_dir;
+    DeviceRestore restore_device_on_exit;
+    int rc = validate(params, m);
+    if (rc) return rc;
+    if (m == 0) return 0;
+    if (!shard_pos || !shard_dir || !frame_pos || !frame_dir || !frame_status)
+        return fail(BHG_ERR_INVALID_ARGUMENT, "bhg_trace_frame_shard_f64: NULL buffer");
+    if (band_rays < 4 || band_rays % 4 || first_band < 0 || band_stride < 1)
+        return fail(BHG_ERR_INVALID_ARGUMENT, "bhg_trace_frame_shard_f64: band_rays must be a positive multiple of 4, "
+                                              "first_band >= 0, band_stride >= 1");
+    DeviceCtx* c;
+    if ((rc = ensure_device(device, &c))) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (!c->courier_stream) BHG_CUDA(cudaStreamCreateWithFlags(&c->courier_stream, cudaStreamNonBlocking));
+    }
+    const long long nb = (m + band_rays - 1) / band_rays;
+    const size_t vec = (((size_t)m * 24) + 255) & ~(size_t)255, sts = (((size_t)m * 4) + 255) & ~(size_t)255;
+    const size_t cnt = ((2 * (size_t)nb + 2) * 4 + 255) & ~(size_t)255;   // band_done, claimed, n_claimed, error
+    char* scratch = nullptr;
+    BHG_CUDA(cudaMallocAsync((void**)&scratch, 2 * vec + sts + cnt, s));
+    double* o_pos = (double*)scratch;
+    double* o_dir = (double*)(scratch + vec);
+    int32_t* o_st = (int32_t*)(scratch + 2 * vec);
+    int* band_done = (int*)(scratch + 2 * vec + sts);
+    BHG_CUDA(cudaMemsetAsync(band_done, 0, cnt, s));
+    cudaEvent_t ready, delivered;
+    BHG_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    BHG_CUDA(cudaEventCreateWithFlags(&delivered, cudaEventDisableTiming));
+    BHG_CUDA(cudaEventRecord(ready, s));
+    BHG_CUDA(cudaStreamWaitEvent(c->courier_stream, ready, 0));
+    bhg::CourierArgs ca;
+    ca.src_pos = o_pos; ca.src_dir = o_dir; ca.src_status = o_st;
+    ca.dst_pos = frame_pos; ca.dst_dir = frame_dir; ca.dst_status = frame_status;
+    ca.band_done = band_done; ca.m = m; ca.band_rays = band_rays; ca.first_band = first_band; ca.band_stride = band_stride;
+    ca.claimed = band_done + nb;
+    ca.n_claimed = band_done + 2 * nb;
+    ca.error = band_done + 2 * nb + 1;
+    // SMs left to the courier: one SM sustains ~25 GB/s of peer stores (measured, profiles/r2h_courier.txt), a shard of
+    // 1/8 frame needs ~70 GB/s to stay hidden behind its integration
+    int courier_sms = 8;
+    if (const char* e = getenv("BHG_COURIER_SMS")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= c->sm_count / 2) courier_sms = v;
+    }
+    bhg::courier_kernel<<<courier_sms, 1024, 0, c->courier_stream>>>(ca);
+    g_launches.fetch_add(1);
+    BHG_CUDA(cudaGetLastError());
+    BHG_CUDA(cudaEventRecord(delivered, c->courier_stream));
+    ShardHook hook{band_done, band_rays, courier_sms, first_band, entry_is_frame ? band_stride : 0};
+    rc = launch_trace(*c, shard_pos, shard_dir, o_pos, o_dir, o_st, nullptr, nullptr, m, bhg::IN_AOS, params->image_width,
+                      params, s, nullptr, nullptr, &hook);
+    cudaStreamWaitEvent(s, delivered, 0);
+    cudaFreeAsync(scratch, s);
+    cudaEventDestroy(ready);
+    cudaEventDestroy(delivered);
+    return rc;
 }
 
 namespace {

@@ -27,6 +27,10 @@ struct TraceArgs {
     int32_t* status;
     int32_t* counters;     // nullable: [0,n) attempts, [n,2n) accepted
     const int32_t* order;  // nullable permutation
+    // cost binning (cost_key_kernel ...): queue order by predicted cost, used unless *sort_keep != 0 (the bundle was
+    // found coherent in memory order and stays as the caller gave it)
+    const int32_t* sorted;
+    const int* sort_keep;
     unsigned long long* queue_head;
     long long n;
     double rs, r_hor, r_sphere, rtol, atol, max_step, lambda_max;
@@ -45,6 +49,19 @@ struct TraceArgs {
     // Prepared rays (pre-pass, prepare_kernel): initial spherical state, f0 and Hairer's first step of every ray in
     // QUEUE order as planes of double2 (coalesced 16-byte loads on refill); NULL = initialise inside the trace kernel
     double2* prep;
+    // Long rays first (pre-pass): queue slots whose predicted step count is >= HOT_ESTIMATE are listed in hot_list (in
+    // arrival order), flagged in hot_mask (one bit per slot) and served BEFORE the natural queue, which skips them:
+    // a 140-attempt photon-ring ray started in the middle of a launch ends 0.1 ms after everybody else.
+    // Band progress for the courier (courier_kernel): when set, every finished ray bumps band_done[idx / band_rays]
+    // after its exit state is visible device-wide
+    int* band_done;
+    long long band_rays;
+    // Input side of a sharded frame: ray i of the launch is frame ray ((i / map_band) map_stride + map_first) map_band
+    // + i % map_band of the `in` arrays (map_band = 0: identity) - the shard reads its bands in place, no compaction
+    long long map_band, map_first, map_stride;
+    unsigned long long* hot_count;   // [0] = number of listed slots
+    int32_t* hot_list;               // [n]
+    unsigned int* hot_mask;          // [(n + 31) / 32]
     // DISK variant only: first crossing of the equatorial plane with disk_r_in <= r <= disk_r_out
     double disk_r_in, disk_r_out;
     double* disk_xy;  // [n][2], NaN = no hit
@@ -66,6 +83,7 @@ constexpr int MISSED_SPHERE = 5;
 // queue slot -> ray index.  With the image hint, 32 consecutive slots (one warp's fetch when it starts empty)
 // cover a 4 x 8 pixel tile, whose rays have far more similar step counts than 32 pixels of one row.
 __device__ __forceinline__ long long slot_to_ray(const TraceArgs& a, long long slot) {
+    if (a.sorted && !__ldg(a.sort_keep)) return (long long)__ldg(a.sorted + slot);
     if (a.order) return (long long)__ldg(a.order + slot);
     if (a.tile_width > 0) {
         // tiles 4 pixels wide x 8 tall (bands of 8 image rows); measured against 8 wide x 4 tall: config 2
@@ -87,6 +105,10 @@ constexpr int PEND_HE = -5;  // both
 // returns false for a ray flagged as missing the sphere (NaN entry position; k holds its flat direction)
 template <int IN>
 __device__ __forceinline__ bool load_ray(const TraceArgs& a, long long idx, double (&x)[3], double (&k)[3]) {
+    if (a.map_band) {
+        const long long q = idx / a.map_band;
+        idx = (q * a.map_stride + a.map_first) * a.map_band + (idx - q * a.map_band);
+    }
     if (IN == IN_AOS_F32) {
         const float* pf = reinterpret_cast<const float*>(a.in);
         const float* df = reinterpret_cast<const float*>(a.in_dir);
@@ -375,6 +397,37 @@ __device__ __forceinline__ int emit_polyline(const TraceArgs& a, long long idx, 
     return pj;
 }
 
+// ---- predicted step count of a ray from its entry state ---------------------------------------------------------------
+// Two quantities govern the adaptive step count (fitted to configs 2 and 5 with the oracle,
+// profiles/r2g_cost_predictor.txt): s = b^2 / 27 M^2 - 1, the distance of the impact parameter b = L / E from the
+// critical one (the photon-sphere winding: +2.2 attempts per halving of |s| for escaping rays, +1.2 for captured ones),
+// and |n_z|, the polar component of the unit normal of the orbital plane: the plane passes the coordinate pole at
+// sin(theta_min) = |n_z|, where the reference's spherical formulation takes small steps (+2.3 attempts per halving
+// for a fly-by, +7 for a ray that winds).  b alone predicts nothing for the 96 % of rays far from critical.
+// Float arithmetic: the estimate only orders the queue, it never touches a result.
+__device__ __forceinline__ float estimate_attempts(const double (&x)[3], const double (&k)[3], double rs) {
+    const float x0 = (float)x[0], x1 = (float)x[1], x2 = (float)x[2];
+    const float k0 = (float)k[0], k1 = (float)k[1], k2 = (float)k[2];
+    const float lx = x1 * k2 - x2 * k1, ly = x2 * k0 - x0 * k2, lz = x0 * k1 - x1 * k0;
+    const float l2 = lx * lx + ly * ly + lz * lz;
+    const float r2 = x0 * x0 + x1 * x1 + x2 * x2;
+    const float xk = x0 * k0 + x1 * k1 + x2 * k2;
+    const float r = sqrtf(r2);
+    const float b2 = l2 * r2 / (xk * xk + (1.0f - (float)rs / r) * l2);   // (L / E)^2
+    const float sgn = b2 * (float)(1.0 / (6.75 * rs * rs)) - 1.0f;        // 27 M^2 = 6.75 rs^2
+    const float u = fabsf(sgn);
+    const float nz = fabsf(lz) * rsqrtf(l2);
+    float base = 12.0f;
+    if (u < 2.0f) {
+        const float lg = 1.0f - __log2f(fmaxf(u, 1e-7f));   // log2(2 / u) >= 0
+        base = sgn > 0.0f ? 19.8f + 2.2f * lg : 33.3f + 1.2f * lg;
+    }
+    float est = base;
+    if (nz < 0.5f) est += (2.26f + 0.158f * (base - 12.0f)) * (-1.0f - __log2f(fmaxf(nz, 1e-7f)));
+    return est < 1e6f ? est : 12.0f;   // NaN / inf from a degenerate entry state
+}
+constexpr float HOT_ESTIMATE = 40.0f;
+
 // ---- prepared rays -------------------------------------------------------------------------------------------------
 // Record of one ray after the pre-pass, NK = 4: {k_t, k_r, k_th, k_ph, r, th, ph, K0[4], h0} = 12 doubles = 6 double2
 // planes; NK = 3: {k_t, k_r, k_ph, r, K0[3], h0} = 8 doubles = 4 planes (t = 0, plane phi = 0).  h0 < 0 encodes the rays
@@ -444,11 +497,17 @@ __global__ void __launch_bounds__(256) prepare_kernel(const TraceArgs a, const C
             for (int c = 0; c < 3; c++) k[c] = k0[c];
         } else {
             if (a.coords) iso_to_schw(a.rs, x0, k0);
+            const float est = a.hot_list ? estimate_attempts(x0, k0, a.rs) : 0.0f;
             if (!init_state<NK>(x0, k0, a.rs, a.r_hor, k, x)) {
                 h0 = -1.0;
             } else if (!all_finite<NK>(k, x)) {
                 h0 = -2.0;
             } else {
+                if (est >= HOT_ESTIMATE) {
+                    const unsigned long long j = atomicAdd(a.hot_count, 1ULL);
+                    a.hot_list[j] = (int32_t)slot;
+                    atomicOr(a.hot_mask + (slot >> 5), 1u << (slot & 31));
+                }
                 Rhs<NK>::eval(k, x, a.rs, K0);
                 h0 = initial_step<NK>(k, x, K0, a.rs, a.rtol, a.atol, a.lambda_max, a.max_step);
                 if (h0 < 0.0) h0 = 0.0;  // cannot happen (steps are non-negative); keeps the status encoding unambiguous
@@ -458,6 +517,100 @@ __global__ void __launch_bounds__(256) prepare_kernel(const TraceArgs a, const C
         Prep<NK>::pack(k, x, K0, h0, v);
 #pragma unroll
         for (int pl = 0; pl < PL; pl++) a.prep[(long long)pl * a.n + slot] = make_double2(v[2 * pl], v[2 * pl + 1]);
+    }
+}
+
+// ---- cost binning for bundles without image order -------------------------------------------------------------------
+// Rays are sorted into COST_BINS classes of estimate_attempts(), costliest first: a warp's 32 lanes then carry similar
+// step counts, so the queue's lanes idle less (config 5 in random planes: -5 %).  A bundle whose memory order is
+// already coherent (neighbouring rays of an image: their step counts agree far better than any estimate) must be left
+// alone (+16 % when sorted): a first pass classifies every 16th group of 32 consecutive rays and, if most groups span
+// at most two neighbouring classes, sets the keep flag; the full key / scatter passes then return at once and the
+// trace kernel serves the caller's order.  All decisions are taken on the device: no host synchronisation.
+// hist layout (ints): [0, COST_BINS) counts, [COST_BINS, 2 COST_BINS) cursors, [2 COST_BINS] coherent groups of the
+// sample, [2 COST_BINS + 1] sampled groups, [2 COST_BINS + 2] keep flag.
+constexpr int COST_BINS = 32;
+constexpr float COST_BIN_WIDTH = 4.0f;
+constexpr int COST_SAMPLE_STRIDE = 16;
+
+template <int IN>
+__device__ __forceinline__ int cost_key(const TraceArgs& a, long long idx) {
+    double x[3], k[3];
+    if (!load_ray<IN>(a, idx, x, k)) return 0;
+    if (a.coords) iso_to_schw(a.rs, x, k);
+    return min(COST_BINS - 1, max(0, (int)(estimate_attempts(x, k, a.rs) * (1.0f / COST_BIN_WIDTH)) - 2));
+}
+
+// pass 0: coherence of a sample of the bundle (one warp per sampled group)
+template <int IN>
+__global__ void __launch_bounds__(256) cost_sample_kernel(const TraceArgs a, int* __restrict__ hist) {
+    const int lane = threadIdx.x & 31;
+    const long long groups = (a.n + 31) / 32;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long g = warp * COST_SAMPLE_STRIDE; g < groups; g += nwarps * COST_SAMPLE_STRIDE) {
+        const long long i = g * 32 + lane;
+        const int key = i < a.n ? cost_key<IN>(a, a.order ? (long long)__ldg(a.order + i) : i) : -1;
+        const int hi = __reduce_max_sync(0xffffffffu, key);
+        const int lo = __reduce_min_sync(0xffffffffu, key < 0 ? COST_BINS : key);
+        if (lane == 0) {
+            atomicAdd(&hist[2 * COST_BINS + 1], 1);
+            if (hi - lo <= 1) atomicAdd(&hist[2 * COST_BINS], 1);
+        }
+    }
+}
+
+__global__ void cost_decide_kernel(int* __restrict__ hist, int force) {
+    if (threadIdx.x == 0) hist[2 * COST_BINS + 2] = (!force && 2 * hist[2 * COST_BINS] > hist[2 * COST_BINS + 1]) ? 1 : 0;
+}
+
+// pass 1: class of every ray + histogram
+template <int IN>
+__global__ void __launch_bounds__(256) cost_key_kernel(const TraceArgs a, unsigned char* __restrict__ keys,
+                                                       int* __restrict__ hist) {
+    if (hist[2 * COST_BINS + 2]) return;
+    __shared__ int s_hist[COST_BINS];
+    if (threadIdx.x < COST_BINS) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+        const int key = cost_key<IN>(a, a.order ? (long long)__ldg(a.order + i) : i);
+        keys[i] = (unsigned char)key;
+        atomicAdd(&s_hist[key], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < COST_BINS && s_hist[threadIdx.x]) atomicAdd(&hist[threadIdx.x], s_hist[threadIdx.x]);
+}
+
+// cursor[key] = first queue slot of bin `key`, costliest bin first
+__global__ void cost_offsets_kernel(int* __restrict__ hist) {
+    if (threadIdx.x == 0 && !hist[2 * COST_BINS + 2]) {
+        int acc = 0;
+        for (int key = COST_BINS - 1; key >= 0; key--) {
+            hist[COST_BINS + key] = acc;
+            acc += hist[key];
+        }
+    }
+}
+
+// pass 2: queue order
+__global__ void __launch_bounds__(256) cost_scatter_kernel(long long n, const int32_t* __restrict__ user_order,
+                                                          const unsigned char* __restrict__ keys, int* __restrict__ hist,
+                                                          int32_t* __restrict__ sorted) {
+    if (hist[2 * COST_BINS + 2]) return;
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    int* cursor = hist + COST_BINS;
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); i0 < n; i0 += stride) {
+        const long long i = i0 + lane;
+        const bool valid = i < n;
+        const int key = valid ? (int)keys[i] : -1;
+        // lanes of the same bin share one atomic (consecutive slots inside the bin keep the warp's ray order)
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const int leader = __ffs(peers) - 1;
+        int base = 0;
+        if (valid && lane == leader) base = atomicAdd(&cursor[key], __popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (valid) sorted[base + __popc(peers & ((1u << lane) - 1u))] = user_order ? __ldg(user_order + i) : (int32_t)i;
     }
 }
 
@@ -506,6 +659,15 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
     const int B = a.idle_budget;
     int idle_acc = 0;  // warp-uniform
     const double t_bound = a.lambda_max;
+    // queue = [listed long rays][natural slots, listed ones skipped]; a list longer than n / 8 is no tail problem but
+    // the bulk of the work (a near-critical bundle): it is then ignored
+    long long n_hot = 0;
+    if (PREP && a.hot_list) {
+        n_hot = (long long)*a.hot_count;
+        if (n_hot > (a.n >> 3)) n_hot = -1;
+    }
+    const bool use_hot = n_hot > 0;
+    const long long q_len = a.n + (use_hot ? n_hot : 0);
 
 #pragma unroll
     for (int i = 0; i < NK; i++) {
@@ -531,7 +693,8 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
         if (service) {
             idle_acc = 0;
             // ---------------- finish pending lanes ----------------
-            const unsigned fin = STAGED ? __ballot_sync(FULL, state != LANE_RUNNING && state != LANE_EMPTY) : 0u;
+            const bool was_finishing = state != LANE_RUNNING && state != LANE_EMPTY;
+            const unsigned fin = STAGED ? __ballot_sync(FULL, was_finishing) : 0u;
             const long long fin_idx = idx;
             if (state != LANE_RUNNING && state != LANE_EMPTY) {
                 int final_status = state;
@@ -627,6 +790,15 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
                     __syncwarp();
                 }
             }
+            if (a.band_done) {  // warp-uniform
+                const unsigned done = __ballot_sync(FULL, fin_idx >= 0 && was_finishing);
+                if (done) {
+                    __threadfence();  // this warp's exit states before the counters
+                    const long long band = was_finishing ? fin_idx / a.band_rays : -1;
+                    const unsigned peers = __match_any_sync(FULL, band);
+                    if (was_finishing && lane == __ffs(peers) - 1) atomicAdd(a.band_done + band, __popc(peers));
+                }
+            }
             // ---------------- refill idle lanes ----------------
             if (!exhausted) {
                 const unsigned idle = __ballot_sync(FULL, state == LANE_EMPTY);
@@ -634,10 +806,19 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(a.queue_head, (unsigned long long)want);
                 base = __shfl_sync(FULL, base, 0);
-                if (base + (unsigned long long)want >= (unsigned long long)a.n) exhausted = true;
+                if (base + (unsigned long long)want >= (unsigned long long)q_len) exhausted = true;
                 if (state == LANE_EMPTY) {
-                    const long long slot = (long long)base + __popc(idle & lt_mask);
-                    if (slot < a.n) {
+                    long long slot = (long long)base + __popc(idle & lt_mask);
+                    bool take = slot < q_len;
+                    if (use_hot && take) {
+                        if (slot < n_hot) {
+                            slot = (long long)__ldg(a.hot_list + slot);
+                        } else {
+                            slot -= n_hot;
+                            take = !((__ldg(a.hot_mask + (slot >> 5)) >> (slot & 31)) & 1u);  // served from the list
+                        }
+                    }
+                    if (take) {
                         idx = slot_to_ray(a, slot);
                         n_attempt = 0;
                         n_accept = 0;
@@ -743,6 +924,94 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
             }
         }
     }
+}
+
+// ---- courier: delivers finished bands of a shard into the frame owner's memory while the trace kernel runs ----------
+// A few resident blocks on SMs the trace kernel leaves free.  Local band j (band_rays consecutive rays of the compact
+// shard, the last one possibly shorter) is complete when band_done[j] equals its ray count; it then moves as 16-byte
+// vectors to frame band first_band + j * band_stride of the owner's buffers - contiguous hundreds of kilobytes, the
+// shape NVLink likes, instead of 24-byte stores scattered over every SM's service phases.  Polling reads bypass L1.
+struct CourierArgs {
+    const double* src_pos; const double* src_dir; const int32_t* src_status;   // compact shard (local)
+    double* dst_pos; double* dst_dir; int32_t* dst_status;                      // frame (owner's memory)
+    const int* band_done;
+    int* claimed;        // [bands] 0 / 1
+    int* n_claimed;      // bands delivered so far
+    long long m, band_rays, first_band, band_stride;
+    int* error;          // set to 1 if a band never completed (the trace kernel failed): no hang
+};
+
+__device__ __forceinline__ void courier_copy(char* __restrict__ dst, const char* __restrict__ src, long long bytes,
+                                             int tid, int nthreads) {
+    // 16-byte vectors; all offsets / sizes are multiples of 16 (band_rays is a multiple of 4)
+    const long long nvec = bytes >> 4;
+    const int4* s = reinterpret_cast<const int4*>(src);
+    int4* d = reinterpret_cast<int4*>(dst);
+    long long i = tid;
+    for (; i + 3LL * nthreads < nvec; i += 4LL * nthreads) {
+        const int4 v0 = __ldcg(s + i), v1 = __ldcg(s + i + nthreads), v2 = __ldcg(s + i + 2LL * nthreads),
+                   v3 = __ldcg(s + i + 3LL * nthreads);
+        d[i] = v0; d[i + nthreads] = v1; d[i + 2LL * nthreads] = v2; d[i + 3LL * nthreads] = v3;
+    }
+    for (; i < nvec; i += nthreads) d[i] = __ldcg(s + i);
+    const long long tail = bytes & 15;   // status of a partial last band
+    if (tid < tail) dst[(nvec << 4) + tid] = src[(nvec << 4) + tid];
+}
+
+__global__ void __launch_bounds__(1024) courier_kernel(const CourierArgs a) {
+    // Every block carries whole bands and takes ANY completed one (bands complete out of order: one photon-ring ray
+    // holds its band back by a tenth of a millisecond): warp 0 scans the counters 32 bands at a time and claims a ready
+    // band with a compare-and-swap, then all 1024 threads move it.
+    const long long nb = (a.m + a.band_rays - 1) / a.band_rays;
+    const int lane = threadIdx.x & 31;
+    __shared__ long long s_band;
+    long long idle = 0;
+    while (true) {
+        if (threadIdx.x < 32) {
+            long long found = -1;
+            for (long long base = 0; base < nb && found < 0; base += 32) {
+                const long long j = base + lane;
+                bool ready = false;
+                if (j < nb && *(volatile const int*)(a.claimed + j) == 0) {
+                    const long long cnt = (a.m - j * a.band_rays < a.band_rays) ? (a.m - j * a.band_rays) : a.band_rays;
+                    ready = *(volatile const int*)(a.band_done + j) >= (int)cnt;
+                }
+                unsigned mask = __ballot_sync(0xffffffffu, ready);
+                while (mask && found < 0) {
+                    const int l = __ffs(mask) - 1;
+                    int won = 0;
+                    if (lane == l) won = atomicCAS(a.claimed + j, 0, 1) == 0;
+                    won = __shfl_sync(0xffffffffu, won, l);
+                    if (won) found = base + l;
+                    mask &= mask - 1;
+                }
+            }
+            if (found < 0 && *(volatile const int*)a.n_claimed >= (int)nb) found = -2;   // everything is taken: done
+            if (lane == 0) s_band = found;
+        }
+        __syncthreads();
+        const long long j = s_band;
+        __syncthreads();
+        if (j == -2) break;
+        if (j < 0) {
+            __nanosleep(1000);
+            if (++idle > 4000000LL) {   // ~4 s without progress: the producer is gone
+                if (threadIdx.x == 0) atomicExch(a.error, 1);
+                break;
+            }
+            continue;
+        }
+        idle = 0;
+        __threadfence();
+        const long long lo = j * a.band_rays;
+        const long long cnt = (a.m - lo < a.band_rays) ? (a.m - lo) : a.band_rays;
+        const long long dst = (a.first_band + j * a.band_stride) * a.band_rays;
+        courier_copy((char*)(a.dst_pos + 3 * dst), (const char*)(a.src_pos + 3 * lo), cnt * 24, threadIdx.x, blockDim.x);
+        courier_copy((char*)(a.dst_dir + 3 * dst), (const char*)(a.src_dir + 3 * lo), cnt * 24, threadIdx.x, blockDim.x);
+        courier_copy((char*)(a.dst_status + dst), (const char*)(a.src_status + lo), cnt * 4, threadIdx.x, blockDim.x);
+        if (threadIdx.x == 0) atomicAdd(a.n_claimed, 1);
+    }
+    __threadfence_system();
 }
 
 // Standalone generator: entry positions / directions of n camera rays as AoS [n][3] (+ hit flag 0 / MISSED_SPHERE)

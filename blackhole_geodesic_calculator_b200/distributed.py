@@ -298,7 +298,10 @@ def trace_sharded_peer(entry_pos, entry_dir, frame: PeerFrame, *, image_width=0,
                final position in the owner's memory through the mapping (remote `out` pointers + `order`).  No
                second pass at all, but 24-byte remote stores: best at 2 GPUs, ingress-bound at 8
                (profiles/r1q_strong_frame_n8.json);
-      "auto"   "stores" up to 2 ranks, "copy" beyond.
+      "courier" band-cyclic shards like "copy", but ONE trace launch per shard: the kernel leaves two SMs to a courier
+               kernel that moves every completed band into the owner's buffers as contiguous 16-byte vectors while the
+               integration runs (bhg_trace_frame_shard_f64) - no pieces and their tails, nothing exposed at the end;
+      "auto"   "courier".
     sync="flags" (default): arrival flags in the owner's memory, written and awaited with stream memory operations
     (PeerFrame.begin_epoch / end_epoch) - nothing that needs an SM or a collective; sync="nccl": a closing 1-element
     all-reduce orders the owner's stream after every rank's work.  `fence_before` orders every rank's writes after the
@@ -312,7 +315,7 @@ def trace_sharded_peer(entry_pos, entry_dir, frame: PeerFrame, *, image_width=0,
     dev = entry_pos.device
     cur = torch.cuda.current_stream(dev)
     if route == "auto":
-        route = "stores"
+        route = "courier"
     if sync not in ("flags", "nccl"):
         raise ValueError("sync must be 'flags' or 'nccl'")
 
@@ -331,8 +334,8 @@ def trace_sharded_peer(entry_pos, entry_dir, frame: PeerFrame, *, image_width=0,
         else:
             frame.fence()
 
-    if route not in ("copy", "stores"):
-        raise ValueError("route must be 'auto', 'copy' or 'stores'")
+    if route not in ("copy", "stores", "courier"):
+        raise ValueError("route must be 'auto', 'courier', 'copy' or 'stores'")
     if route == "stores":
         order = frame.order(image_width)
         params = api.make_params(**trace_kw)
@@ -344,10 +347,30 @@ def trace_sharded_peer(entry_pos, entry_dir, frame: PeerFrame, *, image_width=0,
         close_frame()
         return frame.tensors()
 
-    plan = frame.copy_plan(image_width)
-    band, m, W, r = plan["band"], plan["m"], frame.world, frame.rank
-    params = api.make_params(image_width=image_width if plan["tiles_ok"] else 0, **trace_kw)
+    if route == "courier":
+        key = ("bands", int(image_width))
+        if key not in frame._order_cache:
+            frame._order_cache[key] = band_plan(frame.n, frame.rank, frame.world, int(image_width))
+        band, _, m, tiles_ok = frame._order_cache[key]
+        plan = None
+    else:
+        plan = frame.copy_plan(image_width)
+        band, m, tiles_ok = plan["band"], plan["m"], plan["tiles_ok"]
+    W, r = frame.world, frame.rank
+    params = api.make_params(image_width=image_width if tiles_ok else 0, **trace_kw)
     open_frame()
+    if route == "courier" and not m:
+        close_frame()
+        return frame.tensors()
+    if m and route == "courier":
+        # ONE trace launch over this rank's bands, read in place from the frame's entry arrays; a courier kernel carries
+        # every finished band to the owner while the integration runs
+        import ctypes
+        frame._check(frame._lib.bhg_trace_frame_shard_f64(entry_pos.data_ptr(), entry_dir.data_ptr(), 1, m,
+                                                          frame.pos_ptr, frame.dir_ptr, frame.status_ptr, band, r, W,
+                                                          ctypes.byref(params), dev.index, cur.cuda_stream))
+        close_frame()
+        return frame.tensors()
     if m:
         side, lib = plan["side"], frame._lib
         nb_local = (m + band - 1) // band

@@ -233,6 +233,21 @@ int bhg_ipc_close(void* ptr, int32_t device);
 int bhg_copy_rows(void* dst, int64_t dst_pitch, const void* src, int64_t src_pitch, int64_t row_bytes, int64_t rows,
                   int32_t device, void* stream);
 
+/* One rank's shard of a frame that lives in another GPU's memory.  The shard is every band_stride-th band of
+ * `band_rays` consecutive rays, starting at band first_band: `m` rays in all (the frame's last band may be shorter).
+ * entry_is_frame = 1: entry_pos / entry_dir are the WHOLE frame's float64 AoS arrays (every rank holds them, as every
+ * Blender process would) and the shard's bands are read in place; 0: they hold the m rays of the shard, compacted.
+ * The exit states are delivered to the same band positions of frame_pos / frame_dir / frame_status (bhg_ipc_open
+ * mappings of the owner's buffers, or local pointers on the owner itself) WHILE the integration runs: the trace
+ * kernel leaves a few SMs to a courier kernel that carries every completed band as contiguous 16-byte vectors over
+ * NVLink.  One trace launch per shard, no pieces, no gather afterwards; asynchronous on `stream`.  band_rays must be a
+ * multiple of 4 (with params->image_width = W: bands of 8 image rows, band_rays = 8 W, keep the tile scheduling).
+ * Replaces nothing in the reference (single process); it is the SURVEY 8(e) gather to the rank that owns the frame. */
+int bhg_trace_frame_shard_f64(const double* entry_pos, const double* entry_dir, int32_t entry_is_frame, int64_t m,
+                              double* frame_pos, double* frame_dir, int32_t* frame_status, int64_t band_rays,
+                              int64_t first_band, int64_t band_stride, const bhg_params* params, int32_t device,
+                              void* stream);
+
 /* Stream-ordered 32-bit flag in device memory (driver stream memory operations, executed by the GPU front end: they
  * need no SM, so they progress while a persistent trace kernel owns every register file).  `addr` may be a
  * bhg_ipc_open mapping: the ranks of a sharded frame post "my shard has arrived" into the frame owner's memory with

@@ -175,8 +175,8 @@ def _nccl_worker(rank, world, port, q):
             peer = []
             # arrival flags by stream memory operations (default) and the NCCL fence, both routes, twice in a row so
             # that the second frame has to wait for the owner's release of the buffers
-            for route, w, chunks, sync in (("stores", 0, 1, "flags"), ("stores", 64, 1, "flags"), ("copy", 0, 1, "flags"),
-                                           ("copy", 64, 3, "nccl"), ("stores", 64, 1, "nccl"), ("stores", 64, 1, "flags")):
+            for route, w, chunks, sync in (("stores", 0, 1, "flags"), ("courier", 64, 1, "flags"), ("copy", 0, 1, "flags"),
+                                           ("copy", 64, 3, "nccl"), ("courier", 0, 1, "nccl"), ("auto", 64, 1, "flags")):
                 if rank == 0:
                     frame.tensors()[2].fill_(-7)
                 res = distributed.trace_sharded_peer(tp, td, frame, image_width=w, route=route, chunks=chunks, sync=sync)
@@ -191,9 +191,16 @@ def _nccl_worker(rank, world, port, q):
             try:
                 res2 = distributed.trace_sharded_peer(tp2, td2, frame2, route="copy", chunks=3)
                 torch.cuda.synchronize()
+                ok2a = True
+                if rank == 0:
+                    ok2a = all(torch.equal(a, b) for a, b in zip(res2, api.trace(tp2, td2)))
+                    res2[2].fill_(-7)
+                dist.barrier()
+                res2 = distributed.trace_sharded_peer(tp2, td2, frame2, route="courier")
+                torch.cuda.synchronize()
                 ok2 = True
                 if rank == 0:
-                    ok2 = all(torch.equal(a, b) for a, b in zip(res2, api.trace(tp2, td2)))
+                    ok2 = ok2a and all(torch.equal(a, b) for a, b in zip(res2, api.trace(tp2, td2)))
             finally:
                 frame2.close()
             if rank == 0:
@@ -221,7 +228,7 @@ def test_peer_frame_single_process_routes_equal_plain_trace():
         ref = api.trace(p, q)
         frame = distributed.PeerFrame(n)
         try:
-            for route, chunks in (("stores", 1), ("copy", 1), ("copy", 3)):
+            for route, chunks in (("courier", 1), ("stores", 1), ("copy", 1), ("copy", 3)):
                 frame.tensors()[2].fill_(-7)
                 got = distributed.trace_sharded_peer(p, q, frame, image_width=width, route=route, chunks=chunks)
                 torch.cuda.synchronize()
@@ -239,7 +246,7 @@ def test_peer_frame_graph_replay_single_process():
     tp, td = torch.from_numpy(pos).cuda(), torch.from_numpy(d).cuda()
     frame = distributed.PeerFrame(tp.shape[0])
     try:
-        for route, chunks in (("stores", 1), ("copy", 2)):
+        for route, chunks in (("stores", 1), ("copy", 2), ("courier", 1)):
             g = distributed.PeerFrameGraph(tp, td, frame, image_width=64, route=route, chunks=chunks)
             try:
                 # new frame in the same static buffers: mirror the rays through the equatorial plane
