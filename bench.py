@@ -257,6 +257,70 @@ def strong_frame(args, dev, local, rank, world, n1_ms):
     return out
 
 
+def animation_100(args, dev, local, rank, world):
+    """Config 4: 100 distinct frames of the orbiting camera (azimuth +3.6 deg per frame), 5 242 880 rays each.  The
+    first (100 // N) N frames go to rank f mod N (distributed.frames_for_rank) and are traced straight from their
+    176-byte camera description into alternating device buffers (no host ray buffers, no collective); the remaining
+    100 mod N frames are each split by 8-row bands over ALL ranks and delivered into rank 0's HBM (courier route)."""
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    from blackhole_geodesic_calculator_b200 import _lib, api, distributed as D, raygen
+
+    n, frames = W * H * SPP, 100
+    lib = _lib.load()
+    params = api.make_params(M=raygen.CFG_M, r_sphere=raygen.CFG_R_SPHERE, rtol=1e-3, atol=1e-6, mode=args.mode)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    bufs = [(torch.empty((n, 3), dtype=torch.float64, device=dev), torch.empty((n, 3), dtype=torch.float64, device=dev),
+             torch.empty(n, dtype=torch.int32, device=dev)) for _ in range(2)]
+
+    def camera(f):
+        cpos = frame_camera_pos(f)
+        cam = api.make_camera(cpos, raygen.look_at_rotation(cpos), W, H * SPP, raygen.CFG_FOV, raygen.CFG_FOV,
+                              seed=raygen.CFG_SEED, jitter="philox")
+        cam.height = H
+        return cam
+
+    full = (frames // world) * world
+    mine = [camera(f) for f in D.frames_for_rank(full, rank, world)]
+    left = [camera(f) for f in range(full, frames)]
+    frame = D.PeerFrame(n, owner=0) if (left and world > 1) else None
+    kw = dict(M=raygen.CFG_M, r_sphere=raygen.CFG_R_SPHERE, rtol=1e-3, atol=1e-6, mode=args.mode)
+
+    def run():
+        for i, cam in enumerate(mine):
+            ep, ed, st = bufs[i & 1]
+            _lib.check(lib.bhg_trace_camera_f64(ctypes.byref(cam), ep.data_ptr(), ed.data_ptr(), st.data_ptr(), None, n,
+                                                ctypes.byref(params), local, stream or None))
+        for cam in left:
+            pos, d, _ = api.generate_rays(cam, n, raygen.CFG_R_SPHERE, device=local)
+            D.trace_sharded_peer(pos, d, frame, image_width=W, route="courier", **kw)
+
+    try:
+        run()   # warm-up (allocator pools, peer mappings)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    finally:
+        if frame is not None:
+            frame.close()
+    ms = float(t)
+    return {"frames": frames, "rays": frames * n, "ms": ms, "value": frames * n / (ms * 1e-3), "unit": "rays/s",
+            "frames_per_rank": len(mine), "leftover_frames_split_by_bands": len(left),
+            "input_bytes_per_frame": 176, "results": "device-resident (two alternating buffer sets per rank)",
+            "ms_per_frame_equivalent": ms / frames}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -410,10 +474,24 @@ def run_b200(args):
     torch.cuda.synchronize(dev)
     cam_times.append(time.perf_counter() - t0)
 
+    # (e) camera in, float32 directions + status out: 16 B/ray over PCIe (the recommended wiring for the RRE / CAM
+    # consumers, which read exit_dir only)
+    f_dir16 = f_out[1]
+    if args.mode == "parity":
+        api.trace_camera_f32(cam, n, device=local, buffers=(None, f_dir16, pin_st))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            api.trace_camera_f32(cam, n, device=local, buffers=(None, f_dir16, pin_st))
+        torch.cuda.synchronize(dev)
+        cam_times.append(time.perf_counter() - t0)
+    else:
+        cam_times.append(float("nan"))
+
     t = torch.tensor([total_ms, e2e_s * 1e3] + [c * 1e3 for c in cam_times], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, cam_full_ms, cam_dir_ms, cam_uv_ms, f32_ms = (float(v) for v in t)
+    total_ms, e2e_ms, cam_full_ms, cam_dir_ms, cam_uv_ms, f32_ms, cam_f32_ms = (float(v) for v in t)
     value = world * n * args.steps / (total_ms * 1e-3)
     e2e_value = world * n * e2e_steps / (e2e_ms * 1e-3)
 
@@ -459,6 +537,9 @@ def run_b200(args):
                                               "h2d_bytes_per_step": 176, "d2h_bytes_per_step": n * 28},
                            "sky_uv_and_status": {"value": world * n * e2e_steps / (cam_uv_ms * 1e-3), "unit": "rays/s",
                                                  "h2d_bytes_per_step": 176, "d2h_bytes_per_step": n * 12},
+                           "dir_f32_and_status": {"value": world * n * e2e_steps / (cam_f32_ms * 1e-3), "unit": "rays/s",
+                                                  "h2d_bytes_per_step": 176, "d2h_bytes_per_step": n * 16,
+                                                  "api": "bhg_trace_camera_f32_host"},
                            "api": "bhg_trace_camera_f64_host / bhg_trace_camera_sky_host: rays generated on the device from the camera struct "
                                   "(next-row 1), pinned numpy outputs"},
             "e2e_f32io": {"value": world * n * e2e_steps / (f32_ms * 1e-3), "unit": "rays/s",
@@ -554,7 +635,15 @@ def run_b200(args):
             strong = strong_frame(args, dev, local, rank, world, float(n1))
         except Exception as e:  # never lose the bench line over the extra section
             strong = {"error": repr(e)[:400]}
+    anim = None
+    if args.mode == "parity" and not args.no_animation:
+        try:
+            anim = animation_100(args, dev, local, rank, world)
+        except Exception as e:
+            anim = {"error": repr(e)[:400]}
     if rank == 0:
+        if anim is not None:
+            line["animation_100"] = anim
         if strong is not None:
             line["strong_frame"] = strong
         print(json.dumps(line), flush=True)
@@ -573,6 +662,7 @@ def main():
     ap.add_argument("--threshold", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tiles", action="store_true", help="do not pass the image_width scheduling hint")
+    ap.add_argument("--no-animation", action="store_true", help="skip the 100-frame animation section (config 4)")
     ap.add_argument("--no-strong", action="store_true", help="skip the single-frame strong-scaling section at N > 1")
     ap.add_argument("--disk", action="store_true", help="also locate equatorial-disk crossings (6 M .. 20 M) in flight")
     args = ap.parse_args()

@@ -95,6 +95,8 @@ _SIGNATURES = {
     "bhg_ipc_close": (ctypes.c_int, [_P, ctypes.c_int32]),
     "bhg_copy_rows": (ctypes.c_int, [_P, ctypes.c_int64, _P, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                      ctypes.c_int32, _P]),
+    "bhg_trace_camera_f32_host": (ctypes.c_int, [ctypes.POINTER(BhgCamera), _P, _P, _P, ctypes.c_int64,
+                                                 ctypes.POINTER(BhgParams), ctypes.c_int32]),
     "bhg_trace_frame_shard_f64": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int64, _P, _P, _P, ctypes.c_int64,
                                                  ctypes.c_int64, ctypes.c_int64, ctypes.POINTER(BhgParams), ctypes.c_int32,
                                                  _P]),

@@ -43,6 +43,15 @@ def make_params(M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, max_step=math.inf, e
                      int(image_width), COORDS[coords])
 
 
+def _check_out(a, shape, dtype, name):
+    """Caller-supplied output buffer: the C ABI receives a raw pointer, so shape, dtype and layout are checked here."""
+    if not isinstance(a, np.ndarray) or a.shape != tuple(shape) or a.dtype != np.dtype(dtype) or not a.flags.c_contiguous \
+            or not a.flags.writeable:
+        raise ValueError(f"{name} must be a writeable C-contiguous numpy array of shape {tuple(shape)} and dtype "
+                         f"{np.dtype(dtype).name}; got {type(a).__name__}"
+                         + (f" {a.shape} {a.dtype}" if isinstance(a, np.ndarray) else ""))
+
+
 def _is_torch(x):
     return type(x).__module__.startswith("torch")
 
@@ -72,6 +81,10 @@ def trace(entry_pos, entry_dir, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, *, m
     """
     params = make_params(M, r_sphere, rtol, atol, max_step, eps_horizon, lambda_max, mode, refill_threshold,
                          image_width, coords)
+    if disk is not None:
+        r_in, r_out = float(disk[0]), float(disk[1])
+        if not (0.0 <= r_in <= r_out and r_out > 0.0 and math.isfinite(r_out)):
+            raise ValueError(f"disk=(r_in, r_out) needs 0 <= r_in <= r_out, r_out > 0 and finite; got {disk}")
     if _is_torch(entry_pos):
         if polyline is not None:
             raise ValueError("polyline output is available for numpy inputs")
@@ -84,16 +97,16 @@ def trace(entry_pos, entry_dir, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, *, m
     n = pos.shape[0]
     if out is not None:
         exit_pos, exit_dir, status = out
-        for a, shp, dt in ((exit_pos, (n, 3), np.float64), (exit_dir, (n, 3), np.float64), (status, (n,), np.int32)):
-            if a.shape != shp or a.dtype != dt or not a.flags.c_contiguous:
-                raise ValueError("out arrays must be C-contiguous exit_pos[N,3] f64, exit_dir[N,3] f64, status[N] i32")
+        _check_out(exit_pos, (n, 3), np.float64, "out[0] (exit_pos)")
+        _check_out(exit_dir, (n, 3), np.float64, "out[1] (exit_dir)")
+        _check_out(status, (n,), np.int32, "out[2] (status)")
     else:
         exit_pos = np.empty((n, 3), dtype=np.float64)
         exit_dir = np.empty((n, 3), dtype=np.float64)
         status = np.empty(n, dtype=np.int32)
     counters = np.empty((2, n), dtype=np.int32) if return_counters else None
     p = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
-    disk_xy = np.empty((n, 2), dtype=np.float64) if disk is not None else None
+    disk_xy = np.full((n, 2), np.nan, dtype=np.float64) if disk is not None else None
     extras = None
     if disk is not None or polyline is not None:
         extras = BhgExtras()
@@ -134,7 +147,7 @@ def _trace_torch(entry_pos, entry_dir, params, return_counters, disk=None):
     exit_dir = torch.empty_like(pos)
     status = torch.empty(n, dtype=torch.int32, device=dev)
     counters = torch.empty((2, n), dtype=torch.int32, device=dev) if return_counters else None
-    disk_xy = torch.empty((n, 2), dtype=torch.float64, device=dev) if disk is not None else None
+    disk_xy = torch.full((n, 2), float("nan"), dtype=torch.float64, device=dev) if disk is not None else None
     extras = BhgExtras(float(disk[0]), float(disk[1]), disk_xy.data_ptr()) if disk is not None else None
     trace_device(pos.data_ptr(), dirs.data_ptr(), exit_pos.data_ptr(), exit_dir.data_ptr(), status.data_ptr(),
                  counters.data_ptr() if counters is not None else None, None, n, LAYOUT_AOS, params,
@@ -220,6 +233,10 @@ def trace_camera(cam: BhgCamera, n, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, 
     else:
         if buffers is not None:
             ep, ed, st = buffers
+            if want_pos:
+                _check_out(ep, (n, 3), np.float64, "buffers[0] (exit_pos)")
+            _check_out(ed, (n, 3), np.float64, "buffers[1] (exit_dir)")
+            _check_out(st, (n,), np.int32, "buffers[2] (status)")
         else:
             ep = np.empty((n, 3), dtype=np.float64) if want_pos else None
             ed = np.empty((n, 3), dtype=np.float64)
@@ -231,6 +248,30 @@ def trace_camera(cam: BhgCamera, n, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, 
     if return_counters:
         return ep, ed, st, cnt
     return ep, ed, st
+
+
+def trace_camera_f32(cam: BhgCamera, n, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, *, max_step=math.inf,
+                     eps_horizon=0.01, lambda_max=None, refill_threshold=0, device=0, want_pos=False, buffers=None):
+    """`trace_camera` with float32 host outputs (bhg_trace_camera_f32_host): FP64 integration, exit states rounded once
+    to float32.  With want_pos=False (default) 16 bytes per ray come back - exit_dir + status, what the RRE / CAM
+    consumers read (RelativisticRenderEngine.py:246, RelativisticRenderEngineCamEdition.py:228).
+    `buffers` = (exit_pos f32 [n,3] | None, exit_dir f32 [n,3], status i32 [n]) C-contiguous (e.g. pinned_empty).
+    Returns (exit_pos or None, exit_dir, status)."""
+    params = make_params(M, r_sphere, rtol, atol, max_step, eps_horizon, lambda_max, "parity", refill_threshold)
+    n = int(n)
+    if buffers is not None:
+        ep, ed, st = buffers
+        _check_out(ed, (n, 3), np.float32, "exit_dir")
+        _check_out(st, (n,), np.int32, "status")
+        if want_pos:
+            _check_out(ep, (n, 3), np.float32, "exit_pos")
+    else:
+        ep = np.empty((n, 3), np.float32) if want_pos else None
+        ed, st = np.empty((n, 3), np.float32), np.empty(n, np.int32)
+    p = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+    _lib.check(_lib.load().bhg_trace_camera_f32_host(ctypes.byref(cam), p(ep) if want_pos else None, p(ed), p(st), n,
+                                                     ctypes.byref(params), int(device)))
+    return (ep if want_pos else None), ed, st
 
 
 def trace_f32(entry_pos, entry_dir, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, *, max_step=math.inf,
@@ -247,6 +288,9 @@ def trace_f32(entry_pos, entry_dir, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e-6, 
     n = pos.shape[0]
     if out is not None:
         exit_pos, exit_dir, status = out
+        _check_out(exit_pos, (n, 3), np.float32, "out[0] (exit_pos)")
+        _check_out(exit_dir, (n, 3), np.float32, "out[1] (exit_dir)")
+        _check_out(status, (n,), np.int32, "out[2] (status)")
     else:
         exit_pos, exit_dir = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
         status = np.empty(n, np.int32)
@@ -277,6 +321,9 @@ def trace_camera_sky(cam: BhgCamera, n, M=1.0, r_sphere=60.0, rtol=1e-3, atol=1e
     params = make_params(M, r_sphere, rtol, atol, max_step, eps_horizon, lambda_max, mode, refill_threshold)
     n = int(n)
     uv, st = buffers if buffers is not None else (np.empty((n, 2), np.float32), np.empty(n, np.int32))
+    if buffers is not None:
+        _check_out(uv, (n, 2), np.float32, "buffers[0] (uv)")
+        _check_out(st, (n,), np.int32, "buffers[1] (status)")
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     _lib.check(_lib.load().bhg_trace_camera_sky_host(ctypes.byref(cam), p(uv), p(st), n, ctypes.byref(params),
                                                      int(device)))

@@ -874,6 +874,46 @@ int bhg_trace_camera_f64_host(const bhg_camera* cam, double* exit_pos, double* e
     return 0;
 }
 
+int bhg_trace_camera_f32_host(const bhg_camera* cam, float* exit_pos, float* exit_dir, int32_t* status, int64_t n,
+                              const bhg_params* params, int32_t device) {
+    DeviceRestore restore_device_on_exit;
+    int rc = validate(params, n);
+    if (rc) return rc;
+    if (params->mode != BHG_MODE_PARITY)
+        return fail(BHG_ERR_INVALID_ARGUMENT, "bhg_trace_camera_f32_host: parity mode only");
+    bhg::Camera dc;
+    if ((rc = convert_camera(cam, params->r_sphere, &dc))) return rc;
+    if (n > 0 && (!exit_dir || !status)) return fail(BHG_ERR_INVALID_ARGUMENT, "NULL output buffer");
+    DeviceCtx* c;
+    if ((rc = ensure_device(device, &c))) return rc;
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(c->host_mu);
+    const size_t vec = (((size_t)n * 3 * sizeof(float)) + 255) & ~(size_t)255;
+    if ((rc = ensure_stage(c, 2 * vec + (size_t)n * sizeof(int32_t) + 1024))) return rc;
+    DrainStreamsOnExit drain_streams_on_exit{c};
+    char* base = (char*)c->stage;
+    float* d_pout = (float*)(base);
+    float* d_dout = (float*)(base + vec);
+    int32_t* d_status = (int32_t*)(base + 2 * vec);
+    const long long chunk = pick_chunk(n, 8LL * cam->width);
+    int si = 0;
+    for (long long b = 0; b < n; b += chunk, si = (si + 1) % 3) {
+        const long long m = (n - b < chunk) ? (n - b) : chunk;
+        cudaStream_t s = c->streams[si];
+        bhg::Camera cc = dc;
+        cc.first_ray = dc.first_ray + b;
+        // FP64 integration; the trace kernel rounds the exit state to float32 as it stores it (IN_AOS_F32 store path)
+        rc = launch_trace(*c, nullptr, nullptr, exit_pos ? (double*)(d_pout + 3 * b) : nullptr, (double*)(d_dout + 3 * b),
+                          d_status + b, nullptr, nullptr, m, bhg::IN_AOS_F32, camera_image_width(cc), params, s, nullptr, &cc);
+        if (rc) return rc;
+        if (exit_pos) BHG_CUDA(cudaMemcpyAsync(exit_pos + 3 * b, d_pout + 3 * b, (size_t)m * 12, cudaMemcpyDeviceToHost, s));
+        BHG_CUDA(cudaMemcpyAsync(exit_dir + 3 * b, d_dout + 3 * b, (size_t)m * 12, cudaMemcpyDeviceToHost, s));
+        BHG_CUDA(cudaMemcpyAsync(status + b, d_status + b, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+    }
+    for (auto& s : c->streams) BHG_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
 int bhg_sky_uv_f32(const double* exit_dir, const int32_t* status, int64_t n, float* uv, int32_t device, void* stream) {
     DeviceRestore restore_device_on_exit;
     if (n < 0 || (n > 0 && (!exit_dir || !uv))) return fail(BHG_ERR_INVALID_ARGUMENT, "bad n or NULL buffer");
@@ -1040,7 +1080,7 @@ int bhg_trace_frame_shard_f64(const double* entry_pos, const double* entry_dir, 
     ca.error = band_done + 2 * nb + 1;
     // SMs left to the courier: one SM sustains ~25 GB/s of peer stores (measured, profiles/r2h_courier.txt), a shard of
     // 1/8 frame needs ~70 GB/s to stay hidden behind its integration
-    int courier_sms = 8;
+    int courier_sms = 6;
     if (const char* e = getenv("BHG_COURIER_SMS")) {
         const int v = atoi(e);
         if (v >= 1 && v <= c->sm_count / 2) courier_sms = v;

@@ -468,7 +468,7 @@ constexpr int IN_CAMERA = 3;  // prepare_kernel only: rays come from the camera 
 // In the trace kernel this work runs once per warp-service on a latency-bound dependency chain (~1700 instructions,
 // 12 % of all warp time); here it is throughput-bound streaming work for 2048 resident threads per SM.
 template <int NK, int IN>
-__global__ void __launch_bounds__(256) prepare_kernel(const TraceArgs a, const Camera cam, double* __restrict__ ray_pos,
+__global__ void __launch_bounds__(256, 4) prepare_kernel(const TraceArgs a, const Camera cam, double* __restrict__ ray_pos,
                                                       double* __restrict__ ray_dir) {
     constexpr int PL = Prep<NK>::PL;
     for (long long slot = blockIdx.x * (long long)blockDim.x + threadIdx.x; slot < a.n;

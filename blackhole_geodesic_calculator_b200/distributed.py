@@ -64,6 +64,8 @@ def trace_sharded(entry_pos, entry_dir, *, group=None, dst=0, tracer=None, chunk
         pos, d = np.ascontiguousarray(entry_pos[idx]), np.ascontiguousarray(entry_dir[idx])
     if world == 1:
         return tuple(tracer(pos, d, **trace_kw)[:3])
+    # `dst` is a rank of `group`; torch.distributed.gather wants the global rank
+    gdst = dist.get_global_rank(group, dst) if group is not None else dst
     m_max = (n + world - 1) // world          # largest shard; smaller shards are padded
     if chunks is None:
         chunks = 4 if is_torch else 1
@@ -89,8 +91,8 @@ def trace_sharded(entry_pos, entry_dir, *, group=None, dst=0, tracer=None, chunk
             gs = [torch.empty_like(sts) for _ in range(world)]
         else:
             g6 = gs = None
-        works.append(dist.gather(out6, g6, dst=dst, group=group, async_op=True))
-        works.append(dist.gather(sts, gs, dst=dst, group=group, async_op=True))
+        works.append(dist.gather(out6, g6, dst=gdst, group=group, async_op=True))
+        works.append(dist.gather(sts, gs, dst=gdst, group=group, async_op=True))
         gathered.append((g6, gs, out6, sts))  # keep the send buffers alive until the gathers complete
     for w in works:
         w.wait()

@@ -200,6 +200,13 @@ int bhg_trace_camera_f64(const bhg_camera* cam, double* exit_pos, double* exit_d
 int bhg_trace_camera_f64_host(const bhg_camera* cam, double* exit_pos, double* exit_dir, int32_t* status,
                               int32_t* counters, int64_t n, const bhg_params* params, int32_t device);
 
+/* Same with float32 host outputs: FP64 integration, the exit state rounded once to float32 as it is stored (Blender's
+ * mathutils vectors are float32, RelativisticRenderEngine.py:181-182).  exit_pos may be NULL: exit_dir + status are
+ * what the RRE / CAM consumers read (RelativisticRenderEngine.py:246, RelativisticRenderEngineCamEdition.py:228) -
+ * 16 bytes per ray come back over PCIe instead of 52.  Parity mode only. */
+int bhg_trace_camera_f32_host(const bhg_camera* cam, float* exit_pos, float* exit_dir, int32_t* status, int64_t n,
+                              const bhg_params* params, int32_t device);
+
 /* Sky-lookup coordinates of exit directions: replaces the arithmetic of background_hit (RRE.py:366-378,
  * LIM.py:383-408): uv[i] = (-atan2(d_y,d_x)/pi, 2 (1 - acos(d_z)/pi) - 1) as float32 pairs, NaN for rays whose
  * status is captured / start-inside / failed (the reference paints those black without a lookup); status may

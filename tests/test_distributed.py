@@ -92,3 +92,48 @@ def test_band_plan_partitions_the_frame(n, world, width):
         assert tiles_ok == bool(width) and (not tiles_ok or band == 8 * width)
         seen += idx.tolist()
     assert sorted(seen) == list(range(n))
+
+
+def _subgroup_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from blackhole_geodesic_calculator_b200 import raygen
+        from oracle import port as oracle_port
+
+        def tracer(pos, d, **kw):
+            o = oracle_port.trace(pos, d, nthreads=1, **kw)
+            return o["exit_pos"], o["exit_dir"], o["status"]
+
+        group = dist.new_group([1, 2])       # every rank must take part in creating it
+        if rank == 0:
+            q.put(("outside", 0))
+            return
+        pos, d = raygen.config_bundle(32, 32, 1)
+        pos, d = pos[:301], d[:301]
+        # dst is a rank OF THE GROUP: group rank 1 is global rank 2
+        out = D.trace_sharded(pos, d, group=group, dst=1, tracer=tracer, rtol=1e-3, atol=1e-6)
+        if rank == 2:
+            ref = tracer(pos, d, rtol=1e-3, atol=1e-6)
+            ok = all(np.array_equal(a, b, equal_nan=True) for a, b in zip(out, ref))
+            q.put(("ok" if ok else "mismatch", 2))
+        else:
+            q.put(("none" if out is None else "unexpected", 1))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_trace_sharded_subgroup_dst_is_a_group_rank():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_subgroup_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res == [("none", 1), ("ok", 2), ("outside", 0)]

@@ -261,3 +261,53 @@ def test_peer_frame_graph_replay_single_process():
                 g.close()
     finally:
         frame.close()
+
+
+def test_trace_camera_f32_is_the_rounded_f64_result():
+    """bhg_trace_camera_f32_host: FP64 integration, one rounding to float32 on store; 16 B/ray with want_pos=False.
+    Also the buffer checks every entry point that takes caller arrays applies (a wrong dtype must not reach the DMA)."""
+    import numpy as np
+    from blackhole_geodesic_calculator_b200 import api, raygen
+    cam = api.make_camera(raygen.CFG_CAMERA_POS, raygen.look_at_rotation(raygen.CFG_CAMERA_POS), 64, 48, 0.6, 0.6,
+                          seed=7, jitter="philox")
+    n = 64 * 48
+    ep, ed, st = api.trace_camera(cam, n)
+    fp, fd, fs = api.trace_camera_f32(cam, n, want_pos=True)
+    assert np.array_equal(st, fs)
+    assert np.array_equal(fd, ed.astype(np.float32)) and np.array_equal(fp, ep.astype(np.float32), equal_nan=True)
+    none, fd2, fs2 = api.trace_camera_f32(cam, n)
+    assert none is None and np.array_equal(fd2, fd) and np.array_equal(fs2, fs)
+    import pytest
+    with pytest.raises(ValueError):   # float64 arrays handed to the float32 entry point
+        api.trace_camera_f32(cam, n, buffers=(None, np.empty((n, 3)), np.empty(n, np.int32)))
+    with pytest.raises(ValueError):   # short status array
+        api.trace_camera(cam, n, buffers=(np.empty((n, 3)), np.empty((n, 3)), np.empty(n - 1, np.int32)))
+    with pytest.raises(ValueError):   # non-contiguous output
+        api.trace_f32(np.zeros((8, 3), np.float32), np.ones((8, 3), np.float32),
+                      out=(np.empty((8, 6), np.float32)[:, ::2], np.empty((8, 3), np.float32), np.empty(8, np.int32)))
+    with pytest.raises(ValueError):   # disk annulus
+        api.trace(np.array([[30.0, 0, 0]]), np.array([[-1.0, 0, 0]]), disk=(20.0, 6.0))
+
+
+def test_camera_inside_the_sphere_starts_at_the_camera():
+    """the RRE / CAM engines put the camera inside the curved region (RelativisticRenderEngineCamEdition.py:212,
+    camera_location=[1e-5,-10,10] with r_sphere-style region around it): every ray then starts at the camera itself -
+    device generator, host generator and the CAM adapter agree with the oracle on those rays."""
+    import numpy as np
+    from blackhole_geodesic_calculator_b200 import adapters, api, raygen
+    from oracle import port
+    cam_pos = (1e-5, -10.0, 10.0)
+    rot = raygen.look_at_rotation(cam_pos)
+    cam = api.make_camera(cam_pos, rot, 24, 16, 0.8, 0.8, seed=3, jitter="philox")
+    n = 24 * 16
+    pos, d, hit = api.generate_rays(cam, n, 60.0)
+    pos, d = pos.cpu().numpy(), d.cpu().numpy()
+    assert (hit.cpu().numpy() == 0).all() and np.allclose(pos, np.array(cam_pos)[None, :], rtol=0, atol=0)
+    dirs = raygen.camera_rays(24, 16, 1, 0.8, 0.8, rot, 3, "philox")
+    hp, hm = raygen.sphere_entry(cam_pos, dirs, 60.0)
+    assert hm.all() and np.array_equal(hp, pos)
+    ep, ed, st = api.trace_camera(cam, n)
+    o = port.trace(pos, d)
+    assert np.array_equal(st, o["status"]) and (st == 1).any() and (st == 0).any()
+    esc = st == 0
+    assert np.abs(ed[esc] - o["exit_dir"][esc]).max() < 1e-6 and np.abs(ep[esc] - o["exit_pos"][esc]).max() / 60.0 < 1e-6
