@@ -430,6 +430,14 @@ __device__ __forceinline__ double rk45_attempt(const double (&k)[NK], const doub
 // esum = n * err^2 (n = 2 NK components): 0.9 (esum/n)^(-1/10) = (0.9 n^(1/10)) esum^(-1/10), so the division by
 // n costs nothing.  Branch-free clamps: the caller already knows whether the step was accepted (esum < n) or
 // rejected (esum >= n or NaN).
+// step_factor_raw: f = 0.9 err^(-1/5) with esum clamped to [1e-11, 1e9] (NaN -> 1e9): f(1e-11) > 11 is above every
+// acceptance cap, f(1e9) = 0.14 below the rejection floor, so the clamp never changes the final factor; the caller
+// applies min(f, 10 or 1) on acceptance and max(f, 0.2) on rejection.
+template <int N2>
+__device__ __forceinline__ double step_factor_raw(double esum) {
+    constexpr double c = (N2 == 8) ? 0.9 * 1.2311444133449163 : 0.9 * 1.1962311988513155;  // 0.9 * N2^(1/10)
+    return c * inv_tenth_root<false>(min_nn(max_nn(esum, 1e-11), 1e9));
+}
 //   accepted: min(hi, f), hi = 10 (or 1 after a rejection); esum -> 0 gives hi (f(1e-11) > 11)
 template <int N2>
 __device__ __forceinline__ double step_factor_accept(double esum, double hi) {

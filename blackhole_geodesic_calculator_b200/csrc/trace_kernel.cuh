@@ -880,10 +880,13 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
                 h_abs = h;
                 n_attempt++;
                 const double esum = rk45_attempt<NK>(k, x, K, kn, xn, h, a.rs, a.atol_over_rtol, a.inv_rtol2, lut);
+                // 0.9 err^(-1/5), computed ONCE for the accepting and the rejecting lanes of the warp (a warp nearly
+                // always holds both, and the inverse tenth root is ~35 cycles of the attempt)
+                const double raw_factor = step_factor_raw<2 * NK>(esum);
                 // esum = 2 NK (RMS error norm)^2: accepted iff error norm < 1 (rk.py:148)
                 if (lt_nn(esum, 2.0 * NK)) {
                     n_accept++;
-                    const double factor = step_factor_accept<2 * NK>(esum, rejected ? 1.0 : 10.0);
+                    const double factor = min_nn(raw_factor, rejected ? 1.0 : 10.0);
                     // events on the accepted step (ivp.py:134-158).  Horizon (direction 0): a running ray always has
                     // r > r_hor (it starts there and stops at its first crossing), so "g0 >= 0 and g1 <= 0" is just
                     // r_new <= r_hor and the upward branch cannot occur.  Sphere (direction +1): g0 <= 0 and g1 >= 0.
@@ -918,7 +921,7 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
                         if (le_nn(t_bound, t)) state = LAMBDA_EXHAUSTED;
                     }
                 } else {
-                    h_abs *= step_factor_reject<2 * NK>(esum);
+                    h_abs *= max_nn(raw_factor, 0.2);
                     rejected = true;
                 }
             }
