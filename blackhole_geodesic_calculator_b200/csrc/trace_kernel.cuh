@@ -49,7 +49,7 @@ struct TraceArgs {
     // Prepared rays (pre-pass, prepare_kernel): initial spherical state, f0 and Hairer's first step of every ray in
     // QUEUE order as planes of double2 (coalesced 16-byte loads on refill); NULL = initialise inside the trace kernel
     double2* prep;
-    // Long rays first (pre-pass): queue slots whose predicted step count is >= HOT_ESTIMATE are listed in hot_list (in
+    // Long rays first (pre-pass): queue slots whose predicted step count is >= HOT_ESTIMATE (28) are listed in hot_list (in
     // arrival order), flagged in hot_mask (one bit per slot) and served BEFORE the natural queue, which skips them:
     // a 140-attempt photon-ring ray started in the middle of a launch ends 0.1 ms after everybody else.
     // Band progress for the courier (courier_kernel): when set, every finished ray bumps band_done[idx / band_rays]
@@ -426,7 +426,7 @@ __device__ __forceinline__ float estimate_attempts(const double (&x)[3], const d
     if (nz < 0.5f) est += (2.26f + 0.158f * (base - 12.0f)) * (-1.0f - __log2f(fmaxf(nz, 1e-7f)));
     return est < 1e6f ? est : 12.0f;   // NaN / inf from a degenerate entry state
 }
-constexpr float HOT_ESTIMATE = 40.0f;
+constexpr float HOT_ESTIMATE = 28.0f;   // 1.7 % of a config-2 frame, 249 of its 253 rays above 50 attempts (profiles/r2g_cost_predictor.txt)
 
 // ---- prepared rays -------------------------------------------------------------------------------------------------
 // Record of one ray after the pre-pass, NK = 4: {k_t, k_r, k_th, k_ph, r, th, ph, K0[4], h0} = 12 doubles = 6 double2

@@ -2,8 +2,9 @@
 
 CPU restatement of the reference's per-ray Schwarzschild null-geodesic path.
 
-PARITY UNPINNED: the reference (`/root/reference`, bldevries/blackhole_geodesic_calculator)
-holds *no* tests, golden vectors or known answers for this path, and the arithmetic lives
+PARITY UNPINNED (pinned only to README Fig. 5 / 6, tests/test_readme_figures.py): the reference
+(`/root/reference`, bldevries/blackhole_geodesic_calculator) holds *no* tests or golden vectors for
+this path - its only known answers are two figures of the README - and the arithmetic lives
 in the third-party package `curvedpy` (un-vendored, un-pinned; README.md:24 names
 "curvedpy v0.0.1"; not installed and not installable here).  This file therefore restates
 curvedpy's *published* method and anchors it on the reference's call sites:
