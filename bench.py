@@ -257,6 +257,46 @@ def strong_frame(args, dev, local, rank, world, n1_ms):
     return out
 
 
+def other_configs(dev, local, peak_tf):
+    """BASELINE configs 3 and 5 on the same build (parity-test cases; reported here so that the driver's run holds them):
+    device-resident rays, CUDA events, median of 5.  Config 5 in random planes has no image order: it goes through the
+    cost binning."""
+    import torch
+    from blackhole_geodesic_calculator_b200 import api, raygen
+
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize(dev)
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ts.append(e0.elapsed_time(e1))
+        return float(np.median(ts))
+
+    out = {}
+    p3, d3 = raygen.random_impact_bundle(None)
+    bundles = [("config3_1920x1080_random_impact", p3, d3)]
+    for name, inplane in (("config5_near_critical_random_planes", False), ("config5_near_critical_in_plane", True)):
+        p5, d5, _ = raygen.near_critical_bundle(1 << 20, in_plane=inplane)
+        bundles.append((name, p5, d5))
+    for name, p, d in bundles:
+        tp, td = torch.from_numpy(p).to(dev), torch.from_numpy(d).to(dev)
+        _, _, st, cnt = api.trace(tp, td, return_counters=True)
+        att = float(cnt[0].double().sum())
+        integ = float((st != 2).double().sum())
+        ms = timed(lambda: api.trace(tp, td))
+        flop = FLOP_FIXED * integ + FLOP_PER_ATTEMPT * att
+        tf = flop / (ms * 1e-3) / 1e12
+        out[name] = {"rays": int(p.shape[0]), "ms": ms, "rays_per_s": p.shape[0] / (ms * 1e-3),
+                     "attempts_per_ray": att / p.shape[0], "tflops": tf, "frac_of_peak": tf / peak_tf if peak_tf else None}
+        del tp, td
+    return out
+
+
 def animation_100(args, dev, local, rank, world):
     """Config 4: 100 distinct frames of the orbiting camera (azimuth +3.6 deg per frame), 5 242 880 rays each.  The
     first (100 // N) N frames go to rank f mod N (distributed.frames_for_rank) and are traced straight from their
@@ -628,6 +668,11 @@ def run_b200(args):
                                                                  "over all cores (includes starting the pool)")
             except Exception as e:
                 line["cpu_baseline"]["extra_shapes_error"] = str(e)
+            if args.mode == "parity":
+                try:
+                    line["other_configs"] = other_configs(dev, local, peak)
+                except Exception as e:
+                    line["other_configs"] = {"error": repr(e)[:300]}
             try:
                 from oracle import port
                 t0 = time.perf_counter()

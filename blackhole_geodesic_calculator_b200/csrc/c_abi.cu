@@ -378,6 +378,8 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
         a.poly_xyz = ex->poly_xyz;
         a.poly_count = ex->poly_count;
     }
+    // work-queue head: with the pre-pass (the default) it lives in this launch's own scratch, set below; the ring of
+    // kQueueSlots heads serves BHG_PREP=0 only (launches further apart than the ring never overlap on one stream)
     unsigned slot = c.next_slot.fetch_add(1) % kQueueSlots;
     a.queue_head = c.queue_slots + slot;
     BHG_CUDA(cudaMemsetAsync(a.queue_head, 0, sizeof(unsigned long long), stream));
@@ -419,14 +421,17 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
         const size_t mask_bytes = ((((size_t)n + 31) / 32) * 4 + 255) & ~(size_t)255;
         // the tail of a launch is a fixed ~0.05 ms: worth the list (+0.6 % pre-pass work) only below ~30 rays per lane
         const bool hot = hot_enabled() && n <= (1LL << 21);
-        BHG_CUDA(cudaMallocAsync((void**)&a.prep, rec_bytes + (hot ? 256 + mask_bytes + (size_t)n * 4 : 0), stream));
+        BHG_CUDA(cudaMallocAsync((void**)&a.prep, rec_bytes + 256 + (hot ? mask_bytes + (size_t)n * 4 : 0), stream));
+        // header of the scratch: [0] this launch's OWN work-queue head (launches on different streams, or a captured
+        // graph replayed next to eager launches, share nothing), [1] the long-ray count
+        char* hb = (char*)a.prep + rec_bytes;
+        a.queue_head = (unsigned long long*)hb;
         if (hot) {
-            char* hb = (char*)a.prep + rec_bytes;
-            a.hot_count = (unsigned long long*)hb;
+            a.hot_count = (unsigned long long*)hb + 1;
             a.hot_mask = (unsigned int*)(hb + 256);
             a.hot_list = (int32_t*)(hb + 256 + mask_bytes);
-            BHG_CUDA(cudaMemsetAsync(hb, 0, 256 + mask_bytes, stream));
         }
+        BHG_CUDA(cudaMemsetAsync(hb, 0, 256 + (hot ? mask_bytes : 0), stream));
         if (cam && mode == BHG_MODE_PLANE) {  // the orbital-plane frame is rebuilt from the flat entry state at the exit
             BHG_CUDA(cudaMallocAsync((void**)&cam_rays, (size_t)n * 48, stream));
             a.in = cam_rays;

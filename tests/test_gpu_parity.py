@@ -4,6 +4,7 @@
 Tolerances (BASELINE.json north_star): status bit-exact outside |b - 3 sqrt(3) M| <= 1e-2 M; exit position
 within 1e-6 relative (to the sphere radius), exit direction within 1e-6 rad."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -513,3 +514,33 @@ def test_adjudicated_outliers_against_scipy_golden(api):
         print(f"{name}: {len(st)} rays, ill-conditioned {int((cmp_ & ~well).sum())}, steps differ {int((~same).sum())}, "
               f"beyond 1e-6 {int((cmp_ & (dev > 1e-6)).sum())}, beyond the conditioned bound {int(viol.sum())}")
         assert viol.sum() <= 10, (name, np.nonzero(viol)[0], dev[viol], cond[viol])
+
+
+def test_queue_order_features_never_change_a_result():
+    """Cost binning (BHG_BIN), long-rays-first (BHG_HOT) and the pre-pass (BHG_PREP) reorder or relocate work; every ray's
+    arithmetic is its own, so the outputs must be bit-identical whatever is switched on - checked on an unordered
+    near-critical bundle (goes through the binning) and an image-ordered one small enough for the long-ray list."""
+    import hashlib
+    import subprocess
+    import sys
+    code = r"""
+import hashlib, sys
+import numpy as np
+sys.path.insert(0, %r)
+from blackhole_geodesic_calculator_b200 import api, raygen
+h = hashlib.sha256()
+p5, d5, _ = raygen.near_critical_bundle(1 << 16, in_plane=False)
+for a in api.trace(p5, d5, return_counters=True): h.update(np.ascontiguousarray(a).tobytes())
+p2, d2 = raygen.config_bundle(256, 256, 2, jitter="philox")
+for a in api.trace(p2, d2, image_width=256, return_counters=True): h.update(np.ascontiguousarray(a).tobytes())
+for a in api.trace(p2, d2, return_counters=True): h.update(np.ascontiguousarray(a).tobytes())
+print(h.hexdigest())
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = {}
+    for env in ({}, {"BHG_BIN": "0"}, {"BHG_BIN": "2"}, {"BHG_HOT": "0"}, {"BHG_PREP": "0"}):
+        e = dict(os.environ)
+        e.update(env)
+        r = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests[str(env)] = r.stdout.strip().splitlines()[-1]
+    assert len(set(digests.values())) == 1, digests
