@@ -251,7 +251,7 @@ template <int IN>
 void launch_cost_passes(int sample_blocks, int blocks, cudaStream_t stream, const bhg::TraceArgs& a, unsigned char* keys,
                         int* hist, int32_t* sorted, int force) {
     bhg::cost_sample_kernel<IN><<<sample_blocks, 256, 0, stream>>>(a, hist);
-    bhg::cost_decide_kernel<<<1, 32, 0, stream>>>(hist, force);
+    bhg::cost_decide_kernel<<<1, 32, 0, stream>>>(hist, force, a.idle_budget, a.idle_budget < 32 ? a.idle_budget : 32);
     bhg::cost_key_kernel<IN><<<blocks, 256, 0, stream>>>(a, keys, hist);
     bhg::cost_offsets_kernel<<<1, 32, 0, stream>>>(hist);
     bhg::cost_scatter_kernel<<<blocks, 256, 0, stream>>>(a.n, a.order, keys, hist, sorted);
@@ -409,6 +409,7 @@ int launch_trace(DeviceCtx& c, const double* in, const double* in_dir, double* o
         BHG_CUDA(cudaGetLastError());
         a.sorted = sorted;
         a.sort_keep = hist + 2 * bhg::COST_BINS + 2;
+        if (a.refill_threshold == 0 && !getenv("BHG_IDLE_BUDGET")) a.idle_budget_dev = hist + 2 * bhg::COST_BINS + 3;
         if (bm == 2) a.tile_width = 0;
     }
     // ---- pre-pass: prepared rays in queue order (stream-ordered scratch)

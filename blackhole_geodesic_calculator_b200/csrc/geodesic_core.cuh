@@ -194,11 +194,13 @@ __device__ __forceinline__ void sincos_tab(double th, double* s, double* c) {
 // angle_in_range().
 constexpr int SINCOS_LUT_N = 1024;
 __device__ __forceinline__ void sincos_lut(const double2* __restrict__ lut, double th, double* s, double* c) {
+    // 512/pi and pi/512 cut to the high word of a double (scripts/gen_tables.py: same values as T_L_N_OVER_PI, T_L_P1):
+    // immediates of the FMA, so the reduction reads no constant from a register
     const double big = 6755399441055744.0;
-    const double tn = fma(th, TAB(T_L_N_OVER_PI), big);
+    const double tn = fma(th, 0x1.45f3p+7, big);
     const int n = __double2loint(tn);
     const double dn = tn - big;
-    double r = fma(-dn, TAB(T_L_P1), th);
+    double r = fma(-dn, 0x1.921fbp-8, th);
     r = fma(-dn, TAB(T_L_P1T), r);
     const double2 sc = lut[n & (SINCOS_LUT_N - 1)];
     const double z = r * r;

@@ -31,6 +31,7 @@ struct TraceArgs {
     // found coherent in memory order and stays as the caller gave it)
     const int32_t* sorted;
     const int* sort_keep;
+    const int* idle_budget_dev;  // cost binning decided the bundle is incoherent: a smaller idle budget (more refills) pays
     unsigned long long* queue_head;
     long long n;
     double rs, r_hor, r_sphere, rtol, atol, max_step, lambda_max;
@@ -528,7 +529,7 @@ __global__ void __launch_bounds__(256, 4) prepare_kernel(const TraceArgs a, cons
 // at most two neighbouring classes, sets the keep flag; the full key / scatter passes then return at once and the
 // trace kernel serves the caller's order.  All decisions are taken on the device: no host synchronisation.
 // hist layout (ints): [0, COST_BINS) counts, [COST_BINS, 2 COST_BINS) cursors, [2 COST_BINS] coherent groups of the
-// sample, [2 COST_BINS + 1] sampled groups, [2 COST_BINS + 2] keep flag.
+// sample, [2 COST_BINS + 1] sampled groups, [2 COST_BINS + 2] keep flag, [2 COST_BINS + 3] idle budget.
 constexpr int COST_BINS = 32;
 constexpr float COST_BIN_WIDTH = 4.0f;
 constexpr int COST_SAMPLE_STRIDE = 16;
@@ -560,8 +561,15 @@ __global__ void __launch_bounds__(256) cost_sample_kernel(const TraceArgs a, int
     }
 }
 
-__global__ void cost_decide_kernel(int* __restrict__ hist, int force) {
-    if (threadIdx.x == 0) hist[2 * COST_BINS + 2] = (!force && 2 * hist[2 * COST_BINS] > hist[2 * COST_BINS + 1]) ? 1 : 0;
+// [2 COST_BINS + 3] = idle budget of the refill policy: services are cheap since the pre-pass, so a bundle whose lanes
+// finish at very different times refills earlier (32 lane-iterations: -4 % on config 5), a coherent one keeps the
+// budget tuned for tiles (profiles/r2m_budget_probe.txt)
+__global__ void cost_decide_kernel(int* __restrict__ hist, int force, int budget_coherent, int budget_incoherent) {
+    if (threadIdx.x == 0) {
+        const int keep = (!force && 2 * hist[2 * COST_BINS] > hist[2 * COST_BINS + 1]) ? 1 : 0;
+        hist[2 * COST_BINS + 2] = keep;
+        hist[2 * COST_BINS + 3] = keep ? budget_coherent : budget_incoherent;
+    }
 }
 
 // pass 1: class of every ray + histogram
@@ -656,7 +664,7 @@ __global__ void __launch_bounds__(BHG_BLOCK, BHG_MIN_BLOCKS) trace_kernel(const 
     int pj = 0;  // POLY: next polyline sample index
     bool exhausted = false;  // warp-uniform: queue has no more rays
     const int T = a.refill_threshold;
-    const int B = a.idle_budget;
+    const int B = a.idle_budget_dev ? __ldg(a.idle_budget_dev) : a.idle_budget;
     int idle_acc = 0;  // warp-uniform
     const double t_bound = a.lambda_max;
     // queue = [listed long rays][natural slots, listed ones skipped]; a list longer than n / 8 is no tail problem but

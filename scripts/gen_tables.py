@@ -99,9 +99,13 @@ extra = [
 import mpmath
 mpmath.mp.prec = 200
 _p64 = mpmath.pi / 512
-_l_p1 = float.fromhex("0x1.921fb54400000p+0") / 256.0   # 33 significant bits: n * L_P1 is exact in the FMA
+# pi/512 and 512/pi cut to the 20 mantissa bits of a double's HIGH word: such constants are encodable as immediates of
+# an FP64 instruction (no register read, no uniform register), n * L_P1 is exact for every
+# n < 2^32, and the remainder L_P1T carries the other 53 bits
+_l_p1 = float.fromhex("0x1.921fbp-8")
+_l_n_over_pi = float.fromhex("0x1.45f3p+7")
 extra += [
-    ("L_N_OVER_PI", float(512 / mpmath.pi)), ("L_P1", _l_p1), ("L_P1T", float(_p64 - mpmath.mpf(_l_p1))),
+    ("L_N_OVER_PI", _l_n_over_pi), ("L_P1", _l_p1), ("L_P1T", float(_p64 - mpmath.mpf(_l_p1))),
     ("LS1", float(-mpmath.mpf(1) / 6)), ("LS2", float(mpmath.mpf(1) / 120)), ("LC2", float(mpmath.mpf(1) / 24)),
 ]
 lut = [(float(mpmath.sin(n * _p64)), float(mpmath.cos(n * _p64))) for n in range(1024)]
