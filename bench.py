@@ -673,6 +673,34 @@ def run_b200(args):
                     line["other_configs"] = other_configs(dev, local, peak)
                 except Exception as e:
                     line["other_configs"] = {"error": repr(e)[:300]}
+                try:
+                    # the same live check against the REAL scipy arm on samples of configs 3 and 5 (VERDICT r1 task 1)
+                    from blackhole_geodesic_calculator_b200 import raygen
+                    extra = {}
+                    p3, d3 = raygen.random_impact_bundle(None)
+                    sel3 = np.arange(0, p3.shape[0], 199)
+                    p5, d5, _ = raygen.near_critical_bundle(1 << 20, in_plane=False)
+                    sel5 = np.arange(0, 1 << 20, 129)
+                    for name, pp, dd in (("config3_sample", p3[sel3], d3[sel3]), ("config5_random_planes_sample", p5[sel5], d5[sel5])):
+                        _, _, c_out = time_reference(pp, dd, cores)
+                        g = api.trace(pp, dd, return_counters=True)
+                        c_pos, c_dir, c_st, _, c_acc = c_out[:5]
+                        same = (g[3][1] == c_acc)
+                        esc = (c_st == 0) & (g[2] == 0)
+                        dev_ = np.maximum(np.abs(g[0] - c_pos).max(axis=1) / raygen_r_sphere(), np.abs(g[1] - c_dir).max(axis=1))
+                        extra[name] = {"rays": int(pp.shape[0]), "status_equal": bool((g[2] == c_st).all()),
+                                       "accepted_steps_equal_frac": float(same.mean()),
+                                       "escaped_beyond_1e-6": int((dev_[esc] > 1e-6).sum()),
+                                       "escaped_beyond_1e-6_with_equal_steps": int((dev_[esc & same] > 1e-6).sum()),
+                                       "median_dev_escaped": float(np.median(dev_[esc])) if esc.any() else None,
+                                       "max_dev_escaped": float(dev_[esc].max(initial=0.0))}
+                    extra["note"] = ("GPU against the scipy arm on every 199th ray of config 3 and every 129th of config 5 in random "
+                                     "planes; near-critical pole-grazing rays of config 5 are ill-conditioned in the reference's "
+                                     "own formulation (scipy vs its C restatement disagree on the same rays, "
+                                     "profiles/r2a_adjudication.json): the gate is the per-ray conditioning rule of tests/")
+                    line["parity_vs_cpu_sample_other_configs"] = extra
+                except Exception as e:
+                    line["parity_vs_cpu_sample_other_configs"] = {"error": repr(e)[:300]}
             try:
                 from oracle import port
                 t0 = time.perf_counter()
