@@ -220,7 +220,11 @@ def strong_frame(args, dev, local, rank, world, n1_ms):
         variants = [("courier", "flags", W, 1), ("stores", "flags", 0, 1), ("copy", "flags", W, 2), ("courier", "nccl", W, 1)]
         for route, sync, width, chunks in variants:
             if rank == 0:
+                frame.tensors()[0].fill_(float("nan"))
+                frame.tensors()[1].fill_(float("nan"))
                 frame.tensors()[2].fill_(-7)
+                torch.cuda.synchronize(dev)
+            dist.barrier()
             call = lambda: D.trace_sharded_peer(pos0, d0, frame, image_width=width, route=route, sync=sync,
                                                 chunks=chunks, **kw)
             res = call()

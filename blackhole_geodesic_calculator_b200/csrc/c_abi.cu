@@ -142,6 +142,7 @@ struct DeviceCtx {
     size_t stage_bytes = 0;
     cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
     cudaStream_t courier_stream = nullptr;   // bhg_trace_frame_shard_f64 (created on first use)
+    bool courier_loaded = false;             // its kernels are resident (lazy module loading)
     // pinned bounce buffers for pageable user arrays (3 pipeline slots), grow-only
     void* bounce = nullptr;
     size_t bounce_bytes = 0;
@@ -1072,11 +1073,30 @@ int bhg_trace_frame_shard_f64(const double* entry_pos, const double* entry_dir, 
     int32_t* o_st = (int32_t*)(scratch + 2 * vec);
     int* band_done = (int*)(scratch + 2 * vec + sts);
     BHG_CUDA(cudaMemsetAsync(band_done, 0, cnt, s));
+    // Kernels that are waited for must be resident in the context BEFORE anything spins on them: with lazy module
+    // loading the first launch of a kernel may need a context-wide synchronisation, which a spinning courier would
+    // never allow.  cudaFuncGetAttributes loads a kernel; once per device.
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        if (!c->courier_loaded) {
+            cudaFuncAttributes fa;
+            BHG_CUDA(cudaFuncGetAttributes(&fa, bhg::courier_kernel));
+            BHG_CUDA(cudaFuncGetAttributes(&fa, bhg::prepare_kernel<4, bhg::IN_AOS>));
+            BHG_CUDA(cudaFuncGetAttributes(&fa, bhg::prepare_kernel<3, bhg::IN_AOS>));
+            BHG_CUDA(cudaFuncGetAttributes(&fa, bhg::trace_kernel<4, bhg::IN_AOS, false, false, true, false>));
+            BHG_CUDA(cudaFuncGetAttributes(&fa, bhg::trace_kernel<3, bhg::IN_AOS, false, false, true, false>));
+            BHG_CUDA(cudaFuncGetAttributes(&fa, bhg::cost_sample_kernel<bhg::IN_AOS>));
+            BHG_CUDA(cudaFuncGetAttributes(&fa, bhg::cost_key_kernel<bhg::IN_AOS>));
+            BHG_CUDA(cudaFuncGetAttributes(&fa, bhg::cost_decide_kernel));
+            BHG_CUDA(cudaFuncGetAttributes(&fa, bhg::cost_offsets_kernel));
+            BHG_CUDA(cudaFuncGetAttributes(&fa, bhg::cost_scatter_kernel));
+            c->courier_loaded = true;
+        }
+    }
     cudaEvent_t ready, delivered;
     BHG_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
     BHG_CUDA(cudaEventCreateWithFlags(&delivered, cudaEventDisableTiming));
     BHG_CUDA(cudaEventRecord(ready, s));
-    BHG_CUDA(cudaStreamWaitEvent(c->courier_stream, ready, 0));
     bhg::CourierArgs ca;
     ca.src_pos = o_pos; ca.src_dir = o_dir; ca.src_status = o_st;
     ca.dst_pos = frame_pos; ca.dst_dir = frame_dir; ca.dst_status = frame_status;
@@ -1084,21 +1104,33 @@ int bhg_trace_frame_shard_f64(const double* entry_pos, const double* entry_dir, 
     ca.claimed = band_done + nb;
     ca.n_claimed = band_done + 2 * nb;
     ca.error = band_done + 2 * nb + 1;
-    // SMs left to the courier: one SM sustains ~25 GB/s of peer stores (measured, profiles/r2h_courier.txt), a shard of
-    // 1/8 frame needs ~70 GB/s to stay hidden behind its integration
+    // SMs left to the courier: one SM sustains ~25 GB/s of peer stores (measured, profiles/r2h_courier_n*.txt), a shard
+    // of 1/8 frame needs ~70 GB/s to stay hidden behind its integration
     int courier_sms = 6;
     if (const char* e = getenv("BHG_COURIER_SMS")) {
         const int v = atoi(e);
         if (v >= 1 && v <= c->sm_count / 2) courier_sms = v;
     }
-    bhg::courier_kernel<<<courier_sms, 1024, 0, c->courier_stream>>>(ca);
-    g_launches.fetch_add(1);
-    BHG_CUDA(cudaGetLastError());
-    BHG_CUDA(cudaEventRecord(delivered, c->courier_stream));
+    // the trace (memset, binning, pre-pass, persistent kernel) is enqueued FIRST, then the courier on its own stream:
+    // nothing the trace still needs from the driver can be held up by the courier's polling
     ShardHook hook{band_done, band_rays, courier_sms, first_band, entry_is_frame ? band_stride : 0};
     rc = launch_trace(*c, shard_pos, shard_dir, o_pos, o_dir, o_st, nullptr, nullptr, m, bhg::IN_AOS, params->image_width,
                       params, s, nullptr, nullptr, &hook);
-    cudaStreamWaitEvent(s, delivered, 0);
+    if (!rc) {
+        BHG_CUDA(cudaStreamWaitEvent(c->courier_stream, ready, 0));
+        ca.wait_limit = 200000;   // ~0.2 s without a single band completing: stop polling
+        bhg::courier_kernel<<<courier_sms, 1024, 0, c->courier_stream>>>(ca);
+        g_launches.fetch_add(1);
+        BHG_CUDA(cudaGetLastError());
+        BHG_CUDA(cudaEventRecord(delivered, c->courier_stream));
+        BHG_CUDA(cudaStreamWaitEvent(s, delivered, 0));
+        // sweep pass on the caller's stream, after the trace kernel and the courier: delivers every band the courier
+        // did not take (none when the two ran side by side; all of them when the kernels were executed one at a time)
+        ca.wait_limit = 0;
+        bhg::courier_kernel<<<c->sm_count, 1024, 0, s>>>(ca);
+        g_launches.fetch_add(1);
+        BHG_CUDA(cudaGetLastError());
+    }
     cudaFreeAsync(scratch, s);
     cudaEventDestroy(ready);
     cudaEventDestroy(delivered);

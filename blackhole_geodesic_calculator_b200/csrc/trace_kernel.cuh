@@ -950,6 +950,8 @@ struct CourierArgs {
     int* n_claimed;      // bands delivered so far
     long long m, band_rays, first_band, band_stride;
     int* error;          // set to 1 if a band never completed (the trace kernel failed): no hang
+    long long wait_limit;  // microsecond-scale polls without progress before a block gives up (the sweep pass delivers
+                           // what is left); <= 0: sweep pass - take whatever is complete and unclaimed, never wait
 };
 
 __device__ __forceinline__ void courier_copy(char* __restrict__ dst, const char* __restrict__ src, long long bytes,
@@ -1005,12 +1007,10 @@ __global__ void __launch_bounds__(1024) courier_kernel(const CourierArgs a) {
         __syncthreads();
         if (j == -2) break;
         if (j < 0) {
+            if (a.wait_limit <= 0) break;            // sweep pass: nothing complete is left unclaimed
             __nanosleep(1000);
-            if (++idle > 4000000LL) {   // ~4 s without progress: the producer is gone
-                if (threadIdx.x == 0) atomicExch(a.error, 1);
-                break;
-            }
-            continue;
+            if (++idle > a.wait_limit) break;        // no progress (e.g. kernels are being run one at a time, as
+            continue;                                // under a sanitizer): the sweep pass after the trace delivers
         }
         idle = 0;
         __threadfence();

@@ -26,8 +26,26 @@ for route, chunks, w in (("stores", 1, 48), ("copy", 3, 48), ("copy", 2, 0)):
     torch.cuda.synchronize()
     print(route, chunks, w, torch.bincount(got[2].long(), minlength=6).tolist())
 frame.close()
+# round 2: courier route (band counters + courier kernel + in-place band reads), ragged frame included; unordered
+# near-critical bundle (cost binning, scatter, adaptive budget) and a small image-ordered one (long-ray list);
+# float32 camera outputs; isotropic boundary chart
+for n_, w_ in ((tp.shape[0], 48), (8192 + 77, 0)):
+    p_, q_ = tp[:n_].contiguous(), td[:n_].contiguous()
+    if n_ > tp.shape[0]:
+        p_, q_ = tp.repeat(5, 1)[:n_].contiguous(), td.repeat(5, 1)[:n_].contiguous()
+    fr = distributed.PeerFrame(n_)
+    got = distributed.trace_sharded_peer(p_, q_, fr, route="courier", image_width=w_)
+    torch.cuda.synchronize()
+    ref = api.trace(p_, q_)
+    print("courier", n_, w_, all(torch.equal(a, b) for a, b in zip(got, ref)))
+    fr.close()
+p5, d5, _ = raygen.near_critical_bundle(1 << 13, in_plane=False)
+o5 = api.trace(p5, d5, return_counters=True)
+print("binned", np.bincount(o5[2], minlength=6), int(o5[3][0].max()))
+print("f32cam", np.bincount(api.trace_camera_f32(cam, 48 * 40)[2], minlength=6))
+print("iso", np.bincount(api.trace(pos, d, coords="isotropic")[2], minlength=6))
 PY
 for tool in memcheck racecheck initcheck; do
-  timeout 600 compute-sanitizer --tool $tool --error-exitcode 7 python /tmp/san.py > gpurun_out/sanitizer_$tool.log 2>&1; echo "$tool rc=$?" | tee -a gpurun_out/sanitizer_$tool.log
-  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|rc=" gpurun_out/sanitizer_$tool.log | tail -2
+  timeout 600 compute-sanitizer --tool $tool --error-exitcode 7 python /tmp/san.py > gpurun_out/r2r_sanitizer_$tool.log 2>&1; echo "$tool rc=$?" | tee -a gpurun_out/r2r_sanitizer_$tool.log
+  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|rc=" gpurun_out/r2r_sanitizer_$tool.log | tail -2
 done

@@ -178,7 +178,11 @@ def _nccl_worker(rank, world, port, q):
             for route, w, chunks, sync in (("stores", 0, 1, "flags"), ("courier", 64, 1, "flags"), ("copy", 0, 1, "flags"),
                                            ("copy", 64, 3, "nccl"), ("courier", 0, 1, "nccl"), ("auto", 64, 1, "flags")):
                 if rank == 0:
+                    frame.tensors()[0].fill_(float("nan"))
+                    frame.tensors()[1].fill_(float("nan"))
                     frame.tensors()[2].fill_(-7)
+                    torch.cuda.synchronize()
+                dist.barrier()
                 res = distributed.trace_sharded_peer(tp, td, frame, image_width=w, route=route, chunks=chunks, sync=sync)
                 torch.cuda.synchronize()
                 peer.append(None if res is None else [t.clone() for t in res])
@@ -229,6 +233,9 @@ def test_peer_frame_single_process_routes_equal_plain_trace():
         frame = distributed.PeerFrame(n)
         try:
             for route, chunks in (("courier", 1), ("stores", 1), ("copy", 1), ("copy", 3)):
+                # sentinels everywhere: a region a route failed to deliver must not pass on stale, identical data
+                frame.tensors()[0].fill_(float("nan"))
+                frame.tensors()[1].fill_(float("nan"))
                 frame.tensors()[2].fill_(-7)
                 got = distributed.trace_sharded_peer(p, q, frame, image_width=width, route=route, chunks=chunks)
                 torch.cuda.synchronize()
@@ -311,3 +318,21 @@ def test_camera_inside_the_sphere_starts_at_the_camera():
     assert np.array_equal(st, o["status"]) and (st == 1).any() and (st == 0).any()
     esc = st == 0
     assert np.abs(ed[esc] - o["exit_dir"][esc]).max() < 1e-6 and np.abs(ep[esc] - o["exit_pos"][esc]).max() / 60.0 < 1e-6
+
+
+def test_courier_route_as_the_very_first_call_of_a_process():
+    """The courier kernel polls for bands the trace kernel completes.  As the FIRST CUDA work of a process nothing it
+    depends on may still need loading (lazy module loading can wait for a context-wide synchronisation that a polling
+    kernel never grants): every band must arrive, image-ordered, binned and ragged frames alike, with sentinels in the
+    frame so that stale data cannot pass."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "courier_check.py")], capture_output=True, text=True,
+                       timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("courier")]
+    assert len(lines) == 3, r.stdout
+    for l in lines:
+        assert "mismatches [0, 0, 0]" in l and "nan left [0, 0]" in l and l.endswith("unwritten status 0"), l
