@@ -46,6 +46,6 @@ print("f32cam", np.bincount(api.trace_camera_f32(cam, 48 * 40)[2], minlength=6))
 print("iso", np.bincount(api.trace(pos, d, coords="isotropic")[2], minlength=6))
 PY
 for tool in memcheck racecheck initcheck; do
-  timeout 600 compute-sanitizer --tool $tool --error-exitcode 7 python /tmp/san.py > gpurun_out/r2r_sanitizer_$tool.log 2>&1; echo "$tool rc=$?" | tee -a gpurun_out/r2r_sanitizer_$tool.log
-  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|rc=" gpurun_out/r2r_sanitizer_$tool.log | tail -2
+  timeout 420 compute-sanitizer --tool $tool --error-exitcode 7 python /tmp/san.py > gpurun_out/r2v_sanitizer_$tool.log 2>&1; echo "$tool rc=$?" | tee -a gpurun_out/r2v_sanitizer_$tool.log
+  grep -E "ERROR SUMMARY|RACECHECK SUMMARY|rc=" gpurun_out/r2v_sanitizer_$tool.log | tail -2
 done
