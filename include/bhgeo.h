@@ -120,6 +120,9 @@ int bhg_trace_schwarzschild_f64(const double* in, const double* in_dir, double* 
  * hit) receives the first crossing of the equatorial plane z = 0 whose radius lies in [disk_r_in, disk_r_out]:
  * the continuous form of checkHitDisk's polyline scan (LimitedRelativisticRenderEngine.py:283-302,413-438),
  * located on the dense output like the terminal events; crossings after capture / exit do not count.
+ * Within ONE accepted RK step only the first plane crossing is examined (a step spans far less than half an orbit in
+ * theta at the default tolerances; checkHitDisk's scan of a sampled polyline has the same resolution limit at its
+ * sample spacing).  disk_r_in / disk_r_out must satisfy 0 <= disk_r_in <= disk_r_out (BHG_ERR_INVALID_ARGUMENT).
  * Parity mode only.  Never changes exit_pos / exit_dir / status. */
 typedef struct bhg_extras {
     double disk_r_in, disk_r_out; /* same length unit as M; the disk is off unless disk_r_out > 0 and disk_xy != NULL */

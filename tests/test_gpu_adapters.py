@@ -336,3 +336,24 @@ def test_courier_route_as_the_very_first_call_of_a_process():
     assert len(lines) == 3, r.stdout
     for l in lines:
         assert "mismatches [0, 0, 0]" in l and "nan left [0, 0]" in l and l.endswith("unwritten status 0"), l
+
+
+def test_stream_flags_on_one_gpu():
+    """bhg_stream_write32 / bhg_stream_wait_geq32 (driver stream memory operations resolved at run time): a stream
+    that waits for a flag is released by a write issued later on another stream - the arrival / release protocol of
+    the sharded frame, on local memory."""
+    import torch
+    from blackhole_geodesic_calculator_b200 import _lib
+    lib = _lib.load()
+    flag = torch.zeros(4, dtype=torch.int32, device="cuda")
+    out = torch.zeros(1, dtype=torch.int32, device="cuda")
+    a, b = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    _lib.check(lib.bhg_stream_wait_geq32(flag.data_ptr() + 4, 7, 0, a.cuda_stream))     # a: blocked until flag[1] >= 7
+    with torch.cuda.stream(a):
+        out.fill_(1)
+    assert int(out.item()) == 0                                                         # still waiting (item() syncs the default stream only)
+    _lib.check(lib.bhg_stream_write32(flag.data_ptr() + 4, 9, 0, b.cuda_stream))        # b: release
+    a.synchronize()
+    assert int(out.item()) == 1 and flag.tolist() == [0, 9, 0, 0]
+    assert lib.bhg_stream_write32(flag.data_ptr() + 2, 1, 0, b.cuda_stream) != 0        # misaligned address is refused
