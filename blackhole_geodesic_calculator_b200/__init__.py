@@ -5,4 +5,4 @@ from .api import (CAPTURED, ESCAPED, LAMBDA_EXHAUSTED, MISSED_SPHERE, START_INSI
 
 __all__ = ["trace", "trace_device", "trace_camera", "generate_rays", "make_camera", "make_params", "MISSED_SPHERE", "ESCAPED", "CAPTURED", "START_INSIDE_HOLE",
            "LAMBDA_EXHAUSTED", "STEP_FAILED", "STATUS_NAMES"]
-__version__ = "0.1.1"
+__version__ = "0.2.0"

@@ -22,7 +22,8 @@
 extern "C" {
 #endif
 
-#define BHG_VERSION 110 /* 0.1.1: bhg_params.reserved became bhg_params.coords (same layout) */
+#define BHG_VERSION 120 /* 0.2.0: + bhg_trace_frame_shard_f64, bhg_stream_write32 / _wait_geq32, bhg_trace_camera_f32_host
+                           * (0.1.1: bhg_params.reserved became bhg_params.coords, same layout) */
 
 /* per-ray status codes written to `status` */
 enum bhg_status {

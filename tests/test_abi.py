@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_defaults():
     lib = _lib.load()
-    assert lib.bhg_version() == 110
+    assert lib.bhg_version() == 120
     p = _lib.BhgParams()
     lib.bhg_default_params(ctypes.byref(p))
     assert (p.M, p.r_sphere, p.rtol, p.atol, p.eps_horizon, p.mode) == (1.0, 60.0, 1e-3, 1e-6, 0.01, 0)
@@ -145,3 +145,26 @@ int main(void) {
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
     assert out.stdout.startswith("version ")
+
+
+def test_caller_buffers_are_checked_before_a_pointer_reaches_the_c_abi():
+    """every entry point that takes caller arrays validates shape, dtype, contiguity (no GPU needed: the
+    check precedes the library call)."""
+    cam = api.make_camera((120.0, -80.0, 40.0), np.eye(3), 8, 8)
+    n = 64
+    good32, goodst = np.empty((n, 3), np.float32), np.empty(n, np.int32)
+    with pytest.raises(ValueError, match="float32"):
+        api.trace_camera_f32(cam, n, buffers=(None, np.empty((n, 3)), goodst))
+    with pytest.raises(ValueError, match="status"):
+        api.trace_camera(cam, n, buffers=(np.empty((n, 3)), np.empty((n, 3)), np.empty(n - 1, np.int32)))
+    with pytest.raises(ValueError, match="uv"):
+        api.trace_camera_sky(cam, n, buffers=(np.empty((n, 3), np.float32), goodst))
+    with pytest.raises(ValueError, match="C-contiguous"):
+        api.trace_f32(np.zeros((n, 3), np.float32), np.ones((n, 3), np.float32),
+                      out=(np.empty((n, 6), np.float32)[:, ::2], good32, goodst))
+    with pytest.raises(ValueError, match="exit_pos"):
+        api.trace(np.zeros((n, 3)), np.ones((n, 3)), out=(np.empty((n, 3), np.float32), np.empty((n, 3)), goodst))
+    with pytest.raises(ValueError, match="r_in"):
+        api.trace(np.zeros((n, 3)), np.ones((n, 3)), disk=(20.0, 6.0))
+    with pytest.raises(ValueError, match="r_in"):
+        api.trace(np.zeros((n, 3)), np.ones((n, 3)), disk=(0.0, 0.0))
