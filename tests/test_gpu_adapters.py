@@ -240,6 +240,13 @@ def test_peer_frame_single_process_routes_equal_plain_trace():
                 got = distributed.trace_sharded_peer(p, q, frame, image_width=width, route=route, chunks=chunks)
                 torch.cuda.synchronize()
                 assert all(torch.equal(a, b) for a, b in zip(got, ref)), (n, width, route, chunks)
+            # the optional orbital-plane mode through the courier (its finish path re-reads the entry state through the
+            # band mapping of the in-place shard)
+            ref_plane = api.trace(p, q, mode="plane")
+            frame.tensors()[2].fill_(-7)
+            got = distributed.trace_sharded_peer(p, q, frame, image_width=width, route="courier", mode="plane")
+            torch.cuda.synchronize()
+            assert all(torch.equal(a, b) for a, b in zip(got, ref_plane)), (n, width, "courier/plane")
         finally:
             frame.close()
 
