@@ -328,7 +328,21 @@ def animation_100(args, dev, local, rank, world):
     full = (frames // world) * world
     mine = [camera(f) for f in D.frames_for_rank(full, rank, world)]
     left = [camera(f) for f in range(full, frames)]
-    frame = D.PeerFrame(n, owner=0) if (left and world > 1) else None
+    frame, split = None, bool(left and world > 1)
+    if split:
+        try:
+            frame = D.PeerFrame(n, owner=0)
+        except Exception:   # no peer mapping on this box: the leftover frames go to single ranks instead of being split
+            split = False
+        ok = torch.tensor([1 if split else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not int(ok) and frame is not None:
+            frame.close()
+            frame = None
+        split = bool(int(ok))
+    if left and not split:
+        mine += [cam for i, cam in enumerate(left) if i % world == rank]
+        left = []
     kw = dict(M=raygen.CFG_M, r_sphere=raygen.CFG_R_SPHERE, rtol=1e-3, atol=1e-6, mode=args.mode)
 
     def run():
@@ -360,7 +374,7 @@ def animation_100(args, dev, local, rank, world):
             frame.close()
     ms = float(t)
     return {"frames": frames, "rays": frames * n, "ms": ms, "value": frames * n / (ms * 1e-3), "unit": "rays/s",
-            "frames_per_rank": len(mine), "leftover_frames_split_by_bands": len(left),
+            "frames_per_rank": len(mine), "leftover_frames_split_by_bands": len(left) if split or world == 1 else 0,
             "input_bytes_per_frame": 176, "results": "device-resident (two alternating buffer sets per rank)",
             "ms_per_frame_equivalent": ms / frames}
 
